@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's public API for the hot path (same names, argument meaning and
+error behaviour as ITensorQTT / ITensorMPS), bound to the C ABI.  A Julia user keeps calling
+`linsolve(A, b, x0, a0, a1; nsweeps, maxdim, cutoff, ...)`; INTEGRATION.md shows the `ccall` shim.
+
+Everything here runs on the GPU through libqtt_b200.so.  Nothing in this package imports `oracle/`."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
+from .chains import DeviceMPS, DeviceMPO
+
+__all__ = ["linsolve", "dmrg_target", "apply", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+           "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
+           "SOLVER_GMRES", "SOLVER_LANCZOS"]
+
+SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT = 0, 1, 2
+
+
+def _per_sweep(v, nsweeps, ctype, default):
+    if v is None:
+        return None, None
+    if np.isscalar(v):
+        v = [v]
+    v = list(v)
+    vals = [v[min(i, len(v) - 1)] for i in range(nsweeps)]  # tdvp `process_sweeps`: last value repeated
+    arr = (ctype * nsweeps)(*vals)
+    return arr, vals
+
+
+def _as_dev_mps(x, ctx):
+    return (x, False) if isinstance(x, DeviceMPS) else (DeviceMPS(x, ctx), True)
+
+
+def _as_dev_mpo(A, ctx):
+    return (A, False) if isinstance(A, DeviceMPO) else (DeviceMPO(A, ctx), True)
+
+
+def _params(nsweeps, maxdim, mindim, cutoff, solver, a0, a1, tol, krylovdim, maxiter, fixed_matvecs, normalize, outputlevel,
+            target, x0_canonical, svd_max_sweeps=0):
+    if nsweeps is None:
+        raise TypeError("nsweeps is required (as in ITensorMPS `tdvp`)")
+    p = SweepParams()
+    keep = []
+    p.nsweeps = int(nsweeps)
+    for name, val, ct in (("maxdim", maxdim, C.c_int32), ("mindim", mindim, C.c_int32), ("cutoff", cutoff, C.c_double)):
+        arr, _ = _per_sweep(val, p.nsweeps, ct, None)
+        keep.append(arr)
+        setattr(p, name, arr if arr is not None else C.cast(None, C.POINTER(ct)))
+    p.solver = solver
+    if np.iscomplexobj(a0) or np.iscomplexobj(a1):
+        raise NotImplementedError("complex a0/a1 are not supported by this build")
+    p.a0, p.a1, p.tol = float(a0), float(a1), float(tol)
+    p.krylovdim, p.maxiter = int(krylovdim), int(maxiter)
+    p.fixed_matvecs = int(fixed_matvecs or 0)
+    p.normalize = int(bool(normalize))
+    p.outputlevel = int(outputlevel)
+    p.target = float(target)
+    p.svd_max_sweeps = int(svd_max_sweeps)
+    p.x0_canonical = int(bool(x0_canonical))
+    return p, keep
+
+
+def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,
+             maxiter=10, ishermitian=False, normalize=False, outputlevel=0, fixed_matvecs=None, x0_canonical=False,
+             ctx=None, return_info=False, on_device=False):
+    """`linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter, ishermitian)`
+    -- solves (a0 + a1 A) x = b by two-site sweeps with a local GMRES
+    (reference examples/airy_equation/src/linsolve.jl:24-34; call sites airy_equation.jl:429, src/eigsolve_target.jl:4).
+    `ishermitian` is accepted for signature compatibility (KrylovKit still picks GMRES unless isposdef).
+    A, b, x0: lists of host cores or Device* handles.  Returns host cores (or a DeviceMPS if `on_device`)."""
+    ctx = ctx or default_context()
+    dA, fa = _as_dev_mpo(A, ctx)
+    db, fb = _as_dev_mps(b, ctx)
+    dx = x0.clone() if isinstance(x0, DeviceMPS) else DeviceMPS(x0, ctx)
+    p, keep = _params(nsweeps, maxdim, mindim, cutoff, SOLVER_GMRES, a0, a1, tol, krylovdim, maxiter, fixed_matvecs,
+                      normalize, outputlevel, 0.0, x0_canonical)
+    infos = (SweepInfo * max(p.nsweeps, 1))()
+    try:
+        check(ctx.handle, lib.qtt_linsolve(ctx.handle, dA.handle, db.handle, dx.handle, C.byref(p), infos))
+    finally:
+        if fa:
+            dA.free()
+        if fb:
+            db.free()
+    out = dx if on_device else dx.download()
+    if not on_device:
+        dx.free()
+    if return_info:
+        return out, [infos[i].as_dict() for i in range(p.nsweeps)]
+    return out
+
+
+def dmrg_target(A, psi0, *, target_eigenvalue, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-12, krylovdim=30,
+                maxiter=1, normalize=True, outputlevel=0, fixed_matvecs=None, x0_canonical=False, ctx=None,
+                return_info=False, on_device=False):
+    """`dmrg_target(A, psi0; target_eigenvalue, nsweeps, maxdim, cutoff, ...)` (reference src/dmrg_target.jl:1-12) with
+    the Krylov local solver the reference sketches at :14-21 (dense `eigen` of the (4 chi^2)^2 effective operator is
+    infeasible beyond chi ~ 64): restarted Lanczos, Ritz value nearest `target_eigenvalue`."""
+    ctx = ctx or default_context()
+    dA, fa = _as_dev_mpo(A, ctx)
+    dx = psi0.clone() if isinstance(psi0, DeviceMPS) else DeviceMPS(psi0, ctx)
+    p, keep = _params(nsweeps, maxdim, mindim, cutoff, SOLVER_LANCZOS, 0.0, 1.0, tol, krylovdim, maxiter, fixed_matvecs,
+                      normalize, outputlevel, target_eigenvalue, x0_canonical)
+    infos = (SweepInfo * max(p.nsweeps, 1))()
+    try:
+        check(ctx.handle, lib.qtt_dmrg_target(ctx.handle, dA.handle, dx.handle, C.byref(p), infos))
+    finally:
+        if fa:
+            dA.free()
+    out = dx if on_device else dx.download()
+    if not on_device:
+        dx.free()
+    if return_info:
+        return out, [infos[i].as_dict() for i in range(p.nsweeps)]
+    return out
+
+
+def apply(A, psi, *, cutoff=1e-13, maxdim=None, mindim=1, ctx=None, on_device=False):
+    """`apply(A::MPO, psi::MPS; cutoff, maxdim, mindim)` (upstream density-matrix algorithm; reference call sites
+    src/dft.jl:124,131, src/prolongation.jl:44,79).  Output cores carry the MPO's output site index."""
+    ctx = ctx or default_context()
+    dA, fa = _as_dev_mpo(A, ctx)
+    dp, fp = _as_dev_mps(psi, ctx)
+    out = C.c_void_p()
+    try:
+        check(ctx.handle, lib.qtt_apply(ctx.handle, dA.handle, dp.handle, float(cutoff), int(maxdim or 0), int(mindim), C.byref(out)))
+    finally:
+        if fa:
+            dA.free()
+        if fp:
+            dp.free()
+    res = DeviceMPS(ctx=ctx, _handle=out)
+    if on_device:
+        return res
+    cores = res.download()
+    res.free()
+    return cores
+
+
+def inner(x, y, ctx=None):
+    """`inner(x, y)` = <x|y>."""
+    ctx = ctx or default_context()
+    dx, fx = _as_dev_mps(x, ctx)
+    dy, fy = _as_dev_mps(y, ctx)
+    out = (C.c_double * 2)()
+    try:
+        check(ctx.handle, lib.qtt_inner(ctx.handle, dx.handle, dy.handle, out))
+    finally:
+        if fx:
+            dx.free()
+        if fy:
+            dy.free()
+    return complex(out[0], out[1]) if (dx.is_complex or dy.is_complex) else out[0]
+
+
+def _residual(A, x, b, ctx):
+    ctx = ctx or default_context()
+    dA, fa = _as_dev_mpo(A, ctx)
+    dx, fx = _as_dev_mps(x, ctx)
+    db, fb = _as_dev_mps(b, ctx)
+    sq, sqn = C.c_double(), C.c_double()
+    try:
+        check(ctx.handle, lib.qtt_residual(ctx.handle, dA.handle, dx.handle, db.handle, C.byref(sq), C.byref(sqn)))
+    finally:
+        for d, f in ((dA, fa), (dx, fx), (db, fb)):
+            if f:
+                d.free()
+    return sq.value, sqn.value
+
+
+def sqeuclidean(Ax, b, ctx=None):
+    """`sqeuclidean((A, x), b)` (reference src/mps_utils.jl:109-111)."""
+    A, x = Ax
+    return _residual(A, x, b, ctx)[0]
+
+
+def sqeuclidean_normalized(Ax, b, ctx=None):
+    """`sqeuclidean_normalized((A, x), b)` (reference src/mps_utils.jl:113-116)."""
+    A, x = Ax
+    return _residual(A, x, b, ctx)[1]
+
+
+# ------------------------------------------------------------------ fine-grained kernels (tests, ncu, roofline)
+def matvec2_flops(chil, chir, wl, wm, wr, d=2):
+    """F_mv."""
+    return 2 * (chil * (wl * chil) * (d * d * chir) + (wl * d) * (chil * d * chir) * (wm * d)
+                + (wm * d) * (chil * d * chir) * (wr * d) + (wr * chir) * (chil * d * d) * chir)
+
+
+def env_flops(chi, chi2, w, w2, d=2):
+    return 2 * (chi * (w * chi) * (d * chi2) + (w * d) * (chi * chi2) * (w2 * d) + (chi * d) * (w2 * chi2) * chi2)
+
+
+def matvec2(L, W1, W2, R, v, reps=1, ctx=None):
+    """`product(P, v)` = noprime(v*L*W1*W2*R).  L (a, w, a'), R (c, w, c'), W (wl, wr, s, s'), v (a, s1, s2, c).
+    Returns (out, ms_per_rep)."""
+    ctx = ctx or default_context()
+    L, W1, W2, R, v = (as_f(t) for t in (L, W1, W2, R, v))
+    chil, wl = L.shape[0], L.shape[1]
+    chir, wr = R.shape[0], R.shape[1]
+    wm = W1.shape[1]
+    assert L.shape == (chil, wl, chil) and R.shape == (chir, wr, chir)
+    assert W1.shape == (wl, wm, 2, 2) and W2.shape == (wm, wr, 2, 2) and v.shape == (chil, 2, 2, chir)
+    out = np.empty_like(v, order="F")
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_matvec2(ctx.handle, dptr(L), dptr(W1), dptr(W2), dptr(R), dptr(v), dptr(out), chil, chir, wl, wm, wr,
+                                      int(reps), C.byref(ms)))
+    return np.ascontiguousarray(out), ms.value
+
+
+def env_left(L, x, W, reps=1, ctx=None):
+    ctx = ctx or default_context()
+    L, x, W = (as_f(t) for t in (L, x, W))
+    chia, w = L.shape[0], L.shape[1]
+    chib, w2 = x.shape[2], W.shape[1]
+    out = np.empty((chib, w2, chib), order="F")
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_env_left(ctx.handle, dptr(L), dptr(x), dptr(W), dptr(out), chia, chib, w, w2, int(reps), C.byref(ms)))
+    return np.ascontiguousarray(out), ms.value
+
+
+def env_right(R, x, W, reps=1, ctx=None):
+    ctx = ctx or default_context()
+    R, x, W = (as_f(t) for t in (R, x, W))
+    chic, w2 = R.shape[0], R.shape[1]
+    chia, w = x.shape[0], W.shape[0]
+    out = np.empty((chia, w, chia), order="F")
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_env_right(ctx.handle, dptr(R), dptr(x), dptr(W), dptr(out), chia, chic, w, w2, int(reps), C.byref(ms)))
+    return np.ascontiguousarray(out), ms.value
+
+
+def split2(phi, ortho="left", cutoff=0.0, maxdim=None, mindim=1, reps=1, ctx=None):
+    """`replacebond!`: truncated SVD split of phi (a, 2, 2, c).  Returns dict(A, B, sigma, rank, sweeps, truncerr, ms)."""
+    ctx = ctx or default_context()
+    phi = as_f(phi)
+    a, c = phi.shape[0], phi.shape[3]
+    kmax = min(2 * a, 2 * c)
+    A = np.zeros((a, 2, kmax), order="F")
+    B = np.zeros((kmax, 2, c), order="F")
+    sig = np.zeros(kmax)
+    info = (C.c_int32 * 2)()
+    err = C.c_double(0)
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_split2(ctx.handle, dptr(phi), a, c, 0 if ortho == "left" else 1, float(cutoff), int(maxdim or 0),
+                                     int(mindim), dptr(A), dptr(B), dptr(sig), info, C.byref(err), int(reps), C.byref(ms)))
+    k = info[0]
+    # the library wrote packed (a, 2, k) / (k, 2, c) column-major arrays into the front of the buffers
+    Ak = np.ascontiguousarray(A.reshape(-1, order="F")[: a * 2 * k].reshape((a, 2, k), order="F"))
+    Bk = np.ascontiguousarray(B.reshape(-1, order="F")[: k * 2 * c].reshape((k, 2, c), order="F"))
+    return dict(A=Ak, B=Bk, sigma=sig[:k].copy(), rank=k, sweeps=info[1], truncerr=err.value, ms=ms.value)
+
+
+def gemm(A, B, Cin=None, alpha=1.0, beta=0.0, transA=False, transB=False, tile=-1, reps=1, ctx=None):
+    """Row-major C = alpha op(A) op(B) + beta C on the DMMA core (test hook)."""
+    ctx = ctx or default_context()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    Cm = np.zeros((M, N)) if Cin is None else np.ascontiguousarray(Cin, dtype=np.float64).copy()
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_gemm(ctx.handle, int(transA), int(transB), M, N, K, float(alpha), dptr(A), A.shape[1], dptr(B), B.shape[1],
+                                   float(beta), dptr(Cm), N, int(tile), int(reps), C.byref(ms)))
+    return Cm, ms.value
+
+
+def krylov_op(op, V, w, h=None, reps=1, ctx=None):
+    """op 0: h = V^T w; 1: w -= V h; 2: ||w||; 3: one CGS2 step (returns w_orth, h, norm)."""
+    ctx = ctx or default_context()
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64).copy()
+    nvec, ln = V.shape
+    hh = np.zeros(nvec) if h is None else np.ascontiguousarray(h, dtype=np.float64).copy()
+    out = np.zeros(2)
+    ms = C.c_float(0)
+    check(ctx.handle, lib.qtt_krylov_op(ctx.handle, int(op), dptr(V), nvec, ln, dptr(w), dptr(hh), dptr(out), int(reps), C.byref(ms)))
+    return w, hh, out[0], ms.value

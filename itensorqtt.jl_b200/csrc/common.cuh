@@ -1,0 +1,194 @@
+// Internal definitions shared by the libqtt_b200 translation units (sm_100a only, no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+#include <stdexcept>
+#include "../../include/qtt_b200.h"
+
+namespace qtt {
+
+// ------------------------------------------------------------------ errors
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define QTT_CUDA(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      ::qtt::fail(QTT_ERR_CUDA, "CUDA error '%s' at %s:%d: %s", cudaGetErrorString(e__), __FILE__, __LINE__, #expr); \
+  } while (0)
+
+#define QTT_REQUIRE(cond, ...)                           \
+  do {                                                   \
+    if (!(cond)) ::qtt::fail(QTT_ERR_ARG, __VA_ARGS__);  \
+  } while (0)
+
+// ------------------------------------------------------------------ device buffers
+// Planar tensor storage: a real tensor has only `re`; a complex tensor stores the imaginary plane
+// `plane` elements after the real one (planar layout keeps every contraction a real DMMA GEMM).
+struct DBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+struct Ctx;
+
+// Simple stack arena for per-bond scratch (no cudaMalloc inside hot loops).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, top = 0, high = 0;
+  double* alloc(size_t n_elems) {
+    size_t bytes = (n_elems * sizeof(double) + 255) & ~size_t(255);
+    if (top + bytes > cap) fail(QTT_ERR_ALLOC, "workspace arena exhausted: need %zu more bytes (cap %zu)", top + bytes - cap, cap);
+    double* r = reinterpret_cast<double*>(base + top);
+    top += bytes;
+    if (top > high) high = top;
+    return r;
+  }
+  size_t mark() const { return top; }
+  void release(size_t m) { top = m; }
+};
+
+struct Ctx {
+  int device = 0;
+  int sms = 0;
+  int cc_major = 0, cc_minor = 0, clock_khz = 0;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  std::string err;
+  int64_t launches = 0;
+  bool profiling = false;
+  // small device scratch for scalars / flags / partial reductions
+  double* d_scal = nullptr;      // 4096 doubles
+  double* d_partial = nullptr;   // partial reduction buffer
+  size_t partial_cap = 0;
+  unsigned int* d_sync = nullptr;  // grid-barrier counters and flags (256 uints)
+  double* h_scal = nullptr;        // pinned host mirror (4096 doubles)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  void ensure_arena(size_t bytes);
+  double* partial(size_t n);
+};
+
+inline void check_launch(Ctx* c, const char* what) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(QTT_ERR_CUDA, "kernel launch '%s' failed: %s", what, cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------ chains
+struct Mps {
+  Ctx* ctx = nullptr;
+  int n = 0;
+  int dtype = QTT_F64;
+  std::vector<int64_t> chi;    // n+1
+  std::vector<DBuf> core;      // device layout [a][s][c] row-major (c fastest); complex: planar, plane = a*2*c
+  ~Mps();
+};
+
+struct Mpo {
+  Ctx* ctx = nullptr;
+  int n = 0;
+  int dtype = QTT_F64;
+  std::vector<int64_t> w;      // n+1
+  std::vector<DBuf> core;      // device layout [wl][wr][s][t] row-major (t = s_out fastest); complex planar
+  std::vector<std::vector<double>> host;  // host copy in the same layout (tiny; used to build fused W tables)
+  ~Mpo();
+};
+
+void dbuf_reserve(DBuf& b, size_t n_elems);
+void dbuf_free(DBuf& b);
+
+// ------------------------------------------------------------------ GEMM core (gemm_dmma.cu)
+struct GemmDesc {
+  const double* A = nullptr;
+  const double* B = nullptr;
+  double* C = nullptr;
+  int M = 0, N = 0, K = 0;
+  long lda = 0, ldb = 0, ldc = 0;  // row strides (elements) of the matrices AS STORED
+  bool transA = false;             // A stored K x M (row-major) instead of M x K
+  bool transB = false;             // B stored N x K (row-major) instead of K x N
+  int batch = 1;                   // blockIdx.z = b1 + batch * b2
+  long sA = 0, sB = 0, sC = 0;
+  int batch2 = 1;
+  long sA2 = 0, sB2 = 0, sC2 = 0;
+  double alpha = 1.0, beta = 0.0;
+  int tile = -1;                   // -1 = heuristic; otherwise index into the tile-config table
+};
+void gemm(Ctx* ctx, const GemmDesc& d);
+const char* gemm_tile_name(int tile);
+int gemm_num_tiles();
+
+// ------------------------------------------------------------------ permutes (permute.cu)
+// out[perm-ordered dims] = in; dims are ROW-MAJOR extents of `in`; out dim k = in dim perm[k].
+void permute(Ctx* ctx, const double* in, double* out, int nd, const int64_t* dims, const int* perm);
+// interleaved complex <-> planar
+void deinterleave(Ctx* ctx, const double* in_interleaved, double* out_re, double* out_im, size_t n);
+void interleave(Ctx* ctx, const double* in_re, const double* in_im, double* out_interleaved, size_t n);
+
+// ------------------------------------------------------------------ hot-path contractions (contract.cu)
+// Device layouts (all row-major, last index fastest):
+//   L [w][a'][a]  (bra a', ket a)      R [w][c][c']  (ket c, bra c')
+//   x [a][s][c]    phi / v [a][s1][s2][c]
+void build_w12(Ctx* ctx, const double* W1, const double* W2, double* W12, int wl, int wm, int wr);
+void matvec2(Ctx* ctx, const double* L, const double* W12, const double* R, const double* v, double* out,
+             int chil, int chir, int wl, int wr, double* scratch /* >= (wl + wr) * 4 * chil * chir */);
+size_t matvec2_scratch(int chil, int chir, int wl, int wr);
+void env_left(Ctx* ctx, const double* L, const double* x, const double* W, const double* y, double* Lnew,
+              int chia, int chib, int chia_y, int chib_y, int w, int w2, double* scratch);
+void env_right(Ctx* ctx, const double* R, const double* x, const double* W, const double* y, double* Rnew,
+               int chia, int chic, int chia_y, int chic_y, int w, int w2, double* scratch);
+size_t env_scratch(int chia, int chib, int w, int w2);
+
+// ------------------------------------------------------------------ Krylov vector ops (krylov.cu)
+void kry_dots(Ctx* ctx, const double* V, int nvec, size_t len, const double* w, double* h /* device, nvec */);
+void kry_dots_acc(Ctx* ctx, const double* V, int nvec, size_t len, const double* w, double* h /* h += V^T w */);
+void kry_axpys(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign);
+// w += sign * V h and, if nrm2sq_out != null, *nrm2sq_out = ||w_new||^2 (device scalar)
+void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign, double* nrm2sq_out);
+void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out /* device scalar */);
+void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out);
+void kry_axpby(Ctx* ctx, size_t len, double a, const double* x, double b, const double* y, double c, const double* z, double* out);
+
+// ------------------------------------------------------------------ SVD split (svd_jacobi.cu)
+struct SplitResult {
+  int rank = 0;
+  int sweeps = 0;
+  double truncerr = 0.0;
+};
+// One-sided Jacobi on the rows of M (q x p row-major, device): on return Wn (allocated from the ctx arena, k x p) holds
+// the k dominant right singular vectors as orthonormal rows (descending sigma); truncation per NDTensors.truncate!.
+// The caller owns the arena mark taken before the call.
+struct RowSvd {
+  int k = 0;
+  int sweeps = 0;
+  double truncerr = 0.0;
+  double* Wn = nullptr;
+};
+RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps);
+// phi [a][s1][s2][c] (device).  Writes A [a][s1][k] and B [k][s2][c] (device, capacity for k = min(2a, 2c)).
+SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, double cutoff, int maxdim, int mindim,
+                   double* A_out, double* B_out, double* sigma_out /* device, may be null */, int max_sweeps);
+
+}  // namespace qtt
+
+struct qtt_ctx : qtt::Ctx {};
+struct qtt_mps : qtt::Mps {};
+struct qtt_mpo : qtt::Mpo {};

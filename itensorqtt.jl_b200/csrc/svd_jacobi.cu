@@ -1,0 +1,364 @@
+// Site splitting: truncated SVD of the two-site tensor by one-sided (Hestenes) Jacobi + the ITensors truncation rule.
+// Replaces `replacebond!` -> `svd` (LAPACK gesdd) -> `truncate!`.
+//
+// Only the factor that becomes the orthonormal core is needed (U for ortho="left", V for ortho="right"); the other
+// core is one GEMM with phi.  So the rows of Z = phi (ortho right) or Z = phi^T (ortho left) are orthogonalised by plane
+// rotations; on convergence row i of Z is sigma_i v_i^T.  One-sided Jacobi computes small singular values to high
+// RELATIVE accuracy, which the sigma^2-relative cutoffs of the reference (1e-12 ... 1e-15) require -- no Gram matrix.
+//
+// Parallel schedule: round-robin tournament, q/2 disjoint row pairs per round, one warp per pair with both rows held
+// in registers (double2 per lane, coalesced), three warp-shuffle reductions (|zi|^2, |zj|^2, zi.zj) and an in-register
+// rotation.  The whole decomposition (all rounds and sweeps, the convergence test, the descending sort of sigma^2 and
+// the truncation scan) is ONE cooperative persistent kernel with a monotonic-counter grid barrier between rounds, so
+// there is no host round trip until the kept rank is read back.
+#include "common.cuh"
+
+namespace qtt {
+
+void permute(Ctx*, const double*, double*, int, const int64_t*, const int*);
+
+namespace {
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct JacobiArgs {
+  double* Z;       // [q][ld] row-major, ld even, columns >= p are zero
+  int q, p, ld;
+  int max_sweeps;
+  double tol;
+  unsigned* sync;  // [0] barrier counter, [1] spare, [2 + s] rotation count of sweep s
+  double* sig2;    // [q] out: squared singular values, descending
+  int* perm;       // [q] out: row index of the i-th largest
+  double* norms;   // [q] scratch
+  int* info;       // out: [0] kept rank, [1] sweeps used, [2] converged flag
+  double* derr;    // out: [0] truncerr
+  double cutoff;
+  int maxdim, mindim;
+};
+
+__device__ __forceinline__ void rotation(double alpha, double beta, double gamma, double& c, double& s) {
+  double zeta = (beta - alpha) / (2.0 * gamma);
+  double t;
+  if (fabs(zeta) > 1e150) t = 0.5 / zeta;
+  else t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  c = rsqrt(1.0 + t * t);
+  s = c * t;
+}
+
+// register-resident pair rotation: NCH double2 chunks per lane per row (covers p <= 128 * NCH / 2 ... i.e. 64*NCH columns)
+template <int NCH>
+__device__ __forceinline__ bool rotate_pair_reg(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, int lane) {
+  double2 za[NCH], zb[NCH];
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      za[k] = __ldcg(reinterpret_cast<const double2*>(ra + col));
+      zb[k] = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    } else {
+      za[k] = make_double2(0.0, 0.0);
+      zb[k] = make_double2(0.0, 0.0);
+    }
+    alpha += za[k].x * za[k].x + za[k].y * za[k].y;
+    beta += zb[k].x * zb[k].x + zb[k].y * zb[k].y;
+    gamma += za[k].x * zb[k].x + za[k].y * zb[k].y;
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gamma = warp_sum(gamma);
+  double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
+  double c, s;
+  rotation(alpha, beta, gamma, c, s);
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      double2 na = make_double2(c * za[k].x - s * zb[k].x, c * za[k].y - s * zb[k].y);
+      double2 nb = make_double2(s * za[k].x + c * zb[k].x, s * za[k].y + c * zb[k].y);
+      __stcg(reinterpret_cast<double2*>(ra + col), na);
+      __stcg(reinterpret_cast<double2*>(rb + col), nb);
+    }
+  }
+  return true;
+}
+
+// generic two-pass version for long rows
+__device__ __forceinline__ bool rotate_pair_mem(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, int lane) {
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+  for (int col = 2 * lane; col < ld; col += 64) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(ra + col));
+    double2 b = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    alpha += a.x * a.x + a.y * a.y;
+    beta += b.x * b.x + b.y * b.y;
+    gamma += a.x * b.x + a.y * b.y;
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gamma = warp_sum(gamma);
+  double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
+  double c, s;
+  rotation(alpha, beta, gamma, c, s);
+  for (int col = 2 * lane; col < ld; col += 64) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(ra + col));
+    double2 b = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    __stcg(reinterpret_cast<double2*>(ra + col), make_double2(c * a.x - s * b.x, c * a.y - s * b.y));
+    __stcg(reinterpret_cast<double2*>(rb + col), make_double2(s * a.x + c * b.x, s * a.y + c * b.y));
+  }
+  return true;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int GW = gridDim.x * wpb;
+  const int qe = (a.q + 1) & ~1;
+  const int npairs = qe / 2, rounds = qe - 1;
+  unsigned target = 0;
+  int sweeps = 0;
+  int converged = (a.q < 2) ? 1 : 0;
+  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
+    bool rotated = false;
+    for (int r = 0; r < rounds; ++r) {
+      for (int i = gw; i < npairs; i += GW) {
+        int ia, ib;
+        if (i == 0) {
+          ia = r;
+          ib = qe - 1;
+        } else {
+          ia = (r + i) % (qe - 1);
+          ib = (r - i + (qe - 1)) % (qe - 1);
+        }
+        if (ia >= a.q || ib >= a.q) continue;
+        if (ia > ib) {
+          int tmp = ia;
+          ia = ib;
+          ib = tmp;
+        }
+        double* ra = a.Z + (size_t)ia * a.ld;
+        double* rb = a.Z + (size_t)ib * a.ld;
+        bool rot;
+        if constexpr (NCH > 0) rot = rotate_pair_reg<NCH>(ra, rb, a.ld, a.tol, lane);
+        else rot = rotate_pair_mem(ra, rb, a.ld, a.tol, lane);
+        rotated |= rot;
+      }
+      grid_sync(a.sync, target);
+    }
+    if (rotated && lane == 0) atomicAdd(a.sync + 2 + sw, 1u);
+    grid_sync(a.sync, target);
+    sweeps = sw + 1;
+    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
+  }
+  // squared norms of the (now mutually orthogonal) rows
+  for (int i = gw; i < a.q; i += GW) {
+    const double* ri = a.Z + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ld; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  // rank sort, descending, ties by index (stable)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.q; i += gridDim.x * blockDim.x) {
+    double ni = __ldcg(a.norms + i);
+    int rank = 0;
+    for (int j = 0; j < a.q; ++j) {
+      double nj = __ldcg(a.norms + j);
+      rank += (nj > ni) || (nj == ni && j < i);
+    }
+    a.perm[rank] = i;
+    a.sig2[rank] = ni;
+  }
+  grid_sync(a.sync, target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // NDTensors.truncate! on P = sigma^2 descending
+    const int q = a.q;
+    int n = q;
+    double err = 0.0;
+    int maxdim = a.maxdim < q ? a.maxdim : q;
+    int mindim = a.mindim > 1 ? a.mindim : 1;
+    if (q > 1) {
+      while (n > maxdim) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      double scale = 0.0;
+      for (int i = 0; i < q; ++i) scale += __ldcg(a.sig2 + i);
+      if (scale == 0.0) scale = 1.0;
+      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      err /= scale;
+    }
+    if (n < 1) n = 1;
+    a.info[0] = n;
+    a.info[1] = sweeps;
+    a.info[2] = converged;
+    a.derr[0] = err;
+  }
+}
+
+// Wn[i][:] = Z[perm[i]][:] / sqrt(sig2[i])  for i < k   (zero rows stay zero)
+__global__ void gather_normalize_kernel(const double* __restrict__ Z, int ld, int p, const int* __restrict__ perm,
+                                        const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
+  int i = blockIdx.y;
+  if (i >= k) return;
+  double s = sqrt(sig2[i]);
+  double inv = s > 0.0 ? 1.0 / s : 0.0;
+  const double* src = Z + (size_t)perm[i] * ld;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x) Wn[(size_t)i * p + col] = src[col] * inv;
+  if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = s;
+}
+
+// Z[r][0..ld) = src[r][0..p) zero padded
+__global__ void pad_rows_kernel(const double* __restrict__ src, int q, int p, int ld, double* __restrict__ Z) {
+  long total = (long)q * ld;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
+    int r = (int)(o / ld), c = (int)(o % ld);
+    Z[o] = c < p ? src[(long)r * p + c] : 0.0;
+  }
+}
+
+template <int NCH>
+void launch_jacobi(Ctx* ctx, JacobiArgs& a, int grid) {
+  void* args[] = {&a};
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_rows_kernel<NCH>, dim3(grid), dim3(64), args, 0, ctx->stream));
+  ctx->launches++;
+}
+
+}  // namespace
+
+RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+  const int ld = (p + 1) & ~1;
+  const int kmax = q < p ? q : p;
+  if (max_sweeps <= 0) max_sweeps = 40;
+  QTT_REQUIRE(max_sweeps <= 200, "svd_max_sweeps too large");
+  double* Z = ctx->arena.alloc((size_t)q * ld);
+  double* sig2 = ctx->arena.alloc(q);
+  double* norms = ctx->arena.alloc(q);
+  int* perm = reinterpret_cast<int*>(ctx->arena.alloc((q + 1) / 2 + 1));
+  int* info = reinterpret_cast<int*>(ctx->arena.alloc(4));
+  double* derr = ctx->arena.alloc(2);
+  if (ld == p) {
+    QTT_CUDA(cudaMemcpyAsync(Z, M, sizeof(double) * (size_t)q * p, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    pad_rows_kernel<<<ctx->sms * 2, 256, 0, ctx->stream>>>(M, q, p, ld, Z);
+    check_launch(ctx, "pad_rows");
+  }
+  QTT_CUDA(cudaMemsetAsync(ctx->d_sync + 8, 0, sizeof(unsigned) * (2 + 200), ctx->stream));
+  JacobiArgs a;
+  a.Z = Z; a.q = q; a.p = p; a.ld = ld;
+  a.max_sweeps = max_sweeps;
+  a.tol = sqrt((double)p) * 1.1102230246251565e-16;
+  a.sync = ctx->d_sync + 8;
+  a.sig2 = sig2; a.perm = perm; a.norms = norms; a.info = info; a.derr = derr;
+  a.cutoff = cutoff;
+  a.maxdim = maxdim > 0 ? maxdim : kmax;
+  if (a.maxdim > kmax) a.maxdim = kmax;
+  a.mindim = mindim;
+  const int npairs = ((q + 1) & ~1) / 2;
+  int grid = (npairs + 1) / 2;
+  if (grid > ctx->sms) grid = ctx->sms;
+  if (grid < 1) grid = 1;
+  if (ld <= 128) launch_jacobi<2>(ctx, a, grid);
+  else if (ld <= 256) launch_jacobi<4>(ctx, a, grid);
+  else if (ld <= 512) launch_jacobi<8>(ctx, a, grid);
+  else if (ld <= 1024) launch_jacobi<16>(ctx, a, grid);
+  else launch_jacobi<0>(ctx, a, grid);
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi launch failed: %s", cudaGetErrorString(e));
+  }
+  // the kept rank decides every later shape: one small read-back per split
+  int* h_info = reinterpret_cast<int*>(ctx->h_scal);
+  double* h_err = ctx->h_scal + 8;
+  QTT_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  QTT_CUDA(cudaMemcpyAsync(h_err, derr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  RowSvd res;
+  res.k = h_info[0];
+  res.sweeps = h_info[1];
+  res.truncerr = *h_err;
+  if (!h_info[2]) fail(QTT_ERR_NOCONV, "Jacobi SVD did not converge in %d sweeps (q=%d, p=%d)", max_sweeps, q, p);
+  res.Wn = ctx->arena.alloc((size_t)res.k * p);
+  dim3 grid2((p + 255) / 256, res.k);
+  gather_normalize_kernel<<<grid2, 256, 0, ctx->stream>>>(Z, ld, p, perm, sig2, res.k, res.Wn, sigma_out);
+  check_launch(ctx, "gather_normalize");
+  return res;
+}
+
+SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, double cutoff, int maxdim, int mindim, double* A_out,
+                   double* B_out, double* sigma_out, int max_sweeps) {
+  const int m = 2 * chia, n = 2 * chic;
+  size_t mark = ctx->arena.mark();
+  SplitResult res;
+  try {
+    if (ortho == 0) {
+      // rows of phi^T (coalesced shared-memory transpose): A[(a s1)][k] = Wn^T ; B[k][(s2 c)] = Wn . phi
+      double* phiT = ctx->arena.alloc((size_t)m * n);
+      int64_t dims[2] = {m, n};
+      int pm[2] = {1, 0};
+      permute(ctx, phi, phiT, 2, dims, pm);
+      RowSvd r = svd_rows(ctx, phiT, n, m, cutoff, maxdim, mindim, sigma_out, max_sweeps);
+      int64_t dims2[2] = {r.k, m};
+      permute(ctx, r.Wn, A_out, 2, dims2, pm);
+      GemmDesc g;
+      g.A = r.Wn; g.B = phi; g.C = B_out;
+      g.M = r.k; g.N = n; g.K = m;
+      g.lda = m; g.ldb = n; g.ldc = n;
+      gemm(ctx, g);
+      res.rank = r.k; res.sweeps = r.sweeps; res.truncerr = r.truncerr;
+    } else {
+      // B[k][(s2 c)] = Wn ; A[(a s1)][k] = phi . Wn^T
+      RowSvd r = svd_rows(ctx, phi, m, n, cutoff, maxdim, mindim, sigma_out, max_sweeps);
+      QTT_CUDA(cudaMemcpyAsync(B_out, r.Wn, sizeof(double) * (size_t)r.k * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      GemmDesc g;
+      g.A = phi; g.B = r.Wn; g.C = A_out;
+      g.transB = true;
+      g.M = m; g.N = r.k; g.K = n;
+      g.lda = n; g.ldb = n; g.ldc = r.k;
+      gemm(ctx, g);
+      res.rank = r.k; res.sweeps = r.sweeps; res.truncerr = r.truncerr;
+    }
+  } catch (...) {
+    ctx->arena.release(mark);
+    throw;
+  }
+  // Scratch lives in the arena: the consumer kernels are already enqueued on the same stream and the arena is only
+  // re-used by later work on that stream, so releasing here is safe.
+  ctx->arena.release(mark);
+  return res;
+}
+
+}  // namespace qtt

@@ -1,0 +1,606 @@
+// Two-site sweep driver and device-resident local Krylov solvers.
+//
+// Replaces, for this path only:
+//   ITensorMPS `tdvp(solver, P, t=Inf, x0; reverse_step=false, nsite=2, ...)`  -> two_site_sweeps()
+//   `ProjMPO_MPS(A, [b])` environment caches + `position!`                      -> LA/RA/LB/RB arrays below
+//   `proj(P::ProjMPS)` (reference src/linsolve.jl:13-22)                         -> project_rhs()
+//   `KrylovKit.linsolve(P, b, x0, a0, a1; tol, krylovdim, maxiter)` (GMRES)      -> gmres_local()
+//   `KrylovKit.eigsolve` (Lanczos / Krylov-Schur) for `dmrg_target`/`eigsolve_target` -> lanczos_local()
+//   `replacebond!` (SVD + truncate!)                                            -> split2() (svd_jacobi.cu)
+// All three hot loops (sweeps, bonds, Krylov iterations) run here; the only host<->device synchronisation per bond
+// is the read-back of the kept rank after the split (fixed-work mode) plus one per GMRES restart cycle otherwise.
+// GMRES scalars (Hessenberg column, Givens rotations, residual estimate, convergence flag) live in device memory and
+// are advanced by a one-thread kernel; the host polls a pinned, device-written flag to stop enqueuing early.
+#include "common.cuh"
+#include <chrono>
+#include <functional>
+
+namespace qtt {
+
+void kry_dots_acc(Ctx*, const double*, int, size_t, const double*, double*);
+
+namespace {
+
+constexpr int KD_MAX = 62;
+// layout of the scalar block in ctx->d_scal (doubles)
+enum {
+  S_BETA = 0, S_NRES2 = 1, S_R0N2 = 2, S_DONE = 3, S_K = 4, S_NRES = 5, S_THETA = 6, S_TMP = 7,
+  OFF_H1 = 16, OFF_H2 = 16 + 64, OFF_Y = 16 + 128, OFF_GC = 16 + 192, OFF_GS = 16 + 256, OFF_YK = 16 + 320,
+  OFF_COEF = 16 + 384, OFF_R = 512, OFF_END = 512 + 64 * 64
+};
+// pinned host status block (ctx->h_scal + 64 ...)
+enum { H_DONE = 64, H_K = 65, H_BETA = 66, H_READ = 80 };
+
+__device__ __forceinline__ void givens(double f, double g, double& c, double& s, double& r) {
+  if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
+  if (f == 0.0) { c = 0.0; s = g > 0 ? 1.0 : -1.0; r = fabs(g); return; }
+  double h = hypot(f, g);
+  double sg = f > 0 ? 1.0 : -1.0;
+  c = fabs(f) / h;
+  s = sg * g / h;
+  r = sg * h;
+}
+
+// One Arnoldi step's scalar work (KrylovKit GMRES inner loop): fold the shift into the Hessenberg
+// column, apply the stored Givens rotations, create the new one, rotate the rhs, update the residual estimate.
+__global__ void gmres_update_kernel(double* S, int k, double a0, double a1, double tol, int ld, volatile double* hstat) {
+  if (S[S_DONE] != 0.0) return;
+  double nres = sqrt(S[S_NRES2]);
+  S[S_NRES] = nres;
+  double* Rm = S + OFF_R;
+  double* y = S + OFF_Y;
+  double* gc = S + OFF_GC;
+  double* gs = S + OFF_GS;
+  if (k == 1) y[0] = sqrt(S[S_R0N2]);
+  for (int i = 0; i < k; ++i) {
+    double h = S[OFF_H1 + i] + S[OFF_H2 + i];
+    Rm[i * ld + (k - 1)] = (i == k - 1) ? (a0 + a1 * h) : (a1 * h);
+  }
+  for (int i = 0; i < k - 1; ++i) {
+    double t1 = Rm[i * ld + (k - 1)], t2 = Rm[(i + 1) * ld + (k - 1)];
+    Rm[i * ld + (k - 1)] = gc[i] * t1 + gs[i] * t2;
+    Rm[(i + 1) * ld + (k - 1)] = -gs[i] * t1 + gc[i] * t2;
+  }
+  double c, s, r;
+  givens(Rm[(k - 1) * ld + (k - 1)], a1 * nres, c, s, r);
+  gc[k - 1] = c;
+  gs[k - 1] = s;
+  Rm[(k - 1) * ld + (k - 1)] = r;
+  double yk = y[k - 1];
+  y[k - 1] = c * yk;
+  y[k] = -s * yk;
+  double beta = fabs(y[k]);
+  S[S_BETA] = beta;
+  S[S_K] = (double)k;
+  if (!(beta > tol)) S[S_DONE] = 1.0;
+  if (hstat) {
+    hstat[H_K] = (double)k;
+    hstat[H_BETA] = beta;
+    hstat[H_DONE] = S[S_DONE];
+    __threadfence_system();
+  }
+}
+
+// Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
+__global__ void gmres_solve_kernel(double* S, int k, int ld) {
+  double* Rm = S + OFF_R;
+  double* y = S + OFF_Y;
+  double* gc = S + OFF_GC;
+  double* gs = S + OFF_GS;
+  double* yk = S + OFF_YK;
+  double* coef = S + OFF_COEF;
+  for (int i = k - 1; i >= 0; --i) {
+    double acc = y[i];
+    for (int j = i + 1; j < k; ++j) acc -= Rm[i * ld + j] * yk[j];
+    yk[i] = acc / Rm[i * ld + i];
+  }
+  for (int i = 0; i <= k; ++i) coef[i] = 0.0;
+  coef[k] = 1.0;
+  for (int i = k - 1; i >= 0; --i) {
+    double t1 = coef[i], t2 = coef[i + 1];
+    coef[i] = gc[i] * t1 - gs[i] * t2;
+    coef[i + 1] = gs[i] * t1 + gc[i] * t2;
+  }
+  for (int i = 0; i <= k; ++i) coef[i] *= y[k];
+  S[S_R0N2] = y[k] * y[k];
+}
+
+__global__ void set_scalars_kernel(double* p, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void scale_inplace_kernel(double* w, size_t len, const double* nrm2sq) {
+  double inv = rsqrt(*nrm2sq);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (size_t)gridDim.x * blockDim.x) w[e] *= inv;
+}
+
+struct LocalStats {
+  int64_t matvecs = 0;
+  double resid = 0.0;
+  double theta = 0.0;
+  int converged = 0;
+};
+
+using MatvecFn = std::function<void(const double*, double*)>;
+
+struct KrylovWork {
+  double* V = nullptr;  // (kd + 1) x len
+  double* w = nullptr;
+  double* r = nullptr;
+};
+
+void read_scalars(Ctx* ctx, int off, int n, double* out) {
+  QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + H_READ, ctx->d_scal + off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) out[i] = ctx->h_scal[H_READ + i];
+}
+
+// KrylovKit.linsolve(f, b, x0, GMRES(krylovdim, maxiter, tol), a0, a1)  [restated in oracle/sweep.py: gmres_krylovkit]
+// Orthogonalisation is CGS2 (two classical Gram-Schmidt passes = 2 multi-dots + 2 multi-axpys), numerically equivalent
+// to KrylovKit's ModifiedGramSchmidt2 but with one reduction per pass instead of one per basis vector.
+void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, size_t len, double a0, double a1, double tol, int kd,
+                 int maxiter, bool fixed, KrylovWork& ws, LocalStats& st) {
+  double* S = ctx->d_scal;
+  volatile double* hstat = ctx->h_scal;
+  auto vec = [&](int i) { return ws.V + (size_t)i * len; };
+  mv(x, ws.w);
+  st.matvecs++;
+  kry_axpby(ctx, len, 1.0, beff, -a0, x, -a1, ws.w, ws.r);
+  kry_nrm2sq(ctx, ws.r, len, S + S_R0N2);
+  double beta = 0.0;
+  if (!fixed) {
+    double v;
+    read_scalars(ctx, S_R0N2, 1, &v);
+    beta = sqrt(v);
+    st.resid = beta;
+    if (beta < tol) { st.converged = 1; return; }
+  }
+  int numiter = 0;
+  while (numiter < maxiter) {
+    numiter++;
+    set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
+    check_launch(ctx, "set_scalars");
+    kry_scale_to(ctx, ws.r, len, S + S_R0N2, true, vec(0));
+    if (!fixed) hstat[H_DONE] = 0.0;
+    int k;
+    for (k = 1; k <= kd; ++k) {
+      mv(vec(k - 1), ws.w);
+      st.matvecs++;
+      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
+      kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
+      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
+      kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
+      gmres_update_kernel<<<1, 1, 0, ctx->stream>>>(S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
+      check_launch(ctx, "gmres_update");
+      kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k));
+      if (!fixed && hstat[H_DONE] != 0.0) break;
+    }
+    int kfin = kd;
+    if (!fixed) {
+      double v[8];
+      read_scalars(ctx, 0, 8, v);
+      kfin = (int)v[S_K];
+      beta = v[S_BETA];
+      st.resid = beta;
+    }
+    gmres_solve_kernel<<<1, 1, 0, ctx->stream>>>(S, kfin, 64);
+    check_launch(ctx, "gmres_solve");
+    kry_axpys(ctx, ws.V, kfin, len, S + OFF_YK, x, 1.0);
+    if (fixed) return;
+    if (beta > tol) {
+      // residual without another operator application (KrylovKit rotates the basis; here: explicit combination)
+      QTT_CUDA(cudaMemsetAsync(ws.r, 0, sizeof(double) * len, ctx->stream));
+      kry_axpys(ctx, ws.V, kfin + 1, len, S + OFF_COEF, ws.r, 1.0);
+    } else {
+      mv(x, ws.w);
+      st.matvecs++;
+      kry_axpby(ctx, len, 1.0, beff, -a0, x, -a1, ws.w, ws.r);
+      kry_nrm2sq(ctx, ws.r, len, S + S_R0N2);
+      double v;
+      read_scalars(ctx, S_R0N2, 1, &v);
+      beta = sqrt(v);
+      st.resid = beta;
+      if (beta < tol) { st.converged = 1; return; }
+    }
+  }
+}
+
+// ---- Lanczos with full (CGS2) orthogonalisation: local eigen solve of the Krylov `dmrg_target` variant ------------
+// Projected matrix T (k x k, symmetric) is accumulated on the device; its eigen-decomposition (k <= 62) is done by a
+// single-warp cyclic Jacobi kernel; the Ritz vector nearest `target` is assembled with one multi-axpy.
+__global__ void lanczos_store_col_kernel(double* S, int k, int ld) {
+  // column k-1 of the projected matrix from the CGS2 coefficients; subdiagonal = residual norm
+  double* T = S + OFF_R;
+  for (int i = 0; i < k; ++i) {
+    double h = S[OFF_H1 + i] + S[OFF_H2 + i];
+    T[i * ld + (k - 1)] = h;
+    T[(k - 1) * ld + i] = h;
+  }
+  S[S_NRES] = sqrt(S[S_NRES2]);
+}
+
+__global__ void __launch_bounds__(32) ritz_kernel(double* S, int k, int ld, double target, double* ritz_coef) {
+  // cyclic Jacobi eigen-decomposition of the k x k symmetric T in shared memory (k <= 62); lane-parallel row/col updates
+  extern __shared__ double ritz_sm[];
+  double(*A)[65] = reinterpret_cast<double(*)[65]>(ritz_sm);
+  double(*Q)[65] = reinterpret_cast<double(*)[65]>(ritz_sm + 64 * 65);
+  const int lane = threadIdx.x;
+  double* T = S + OFF_R;
+  for (int i = 0; i < k; ++i)
+    for (int j = lane; j < k; j += 32) {
+      A[i][j] = 0.5 * (T[i * ld + j] + T[j * ld + i]);
+      Q[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < k; ++i)
+      for (int j = lane; j < k; j += 32)
+        if (i != j) off += A[i][j] * A[i][j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+    double diag = 0.0;
+    for (int j = lane; j < k; j += 32) diag += A[j][j] * A[j][j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int p = 0; p < k - 1; ++p)
+      for (int q = p + 1; q < k; ++q) {
+        double apq = A[p][q];
+        if (fabs(apq) > 1e-300) {
+          double app = A[p][p], aqq = A[q][q];
+          double zeta = (aqq - app) / (2.0 * apq);
+          double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          double c = rsqrt(1.0 + t * t), s = c * t;
+          __syncwarp();
+          for (int j = lane; j < k; j += 32) {  // rows p, q
+            double x1 = A[p][j], x2 = A[q][j];
+            A[p][j] = c * x1 - s * x2;
+            A[q][j] = s * x1 + c * x2;
+          }
+          __syncwarp();
+          for (int j = lane; j < k; j += 32) {  // columns p, q (+ eigenvectors)
+            double x1 = A[j][p], x2 = A[j][q];
+            A[j][p] = c * x1 - s * x2;
+            A[j][q] = s * x1 + c * x2;
+            double q1 = Q[j][p], q2 = Q[j][q];
+            Q[j][p] = c * q1 - s * q2;
+            Q[j][q] = s * q1 + c * q2;
+          }
+          __syncwarp();
+        }
+      }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int best = 0;
+    double bd = fabs(A[0][0] - target);
+    for (int j = 1; j < k; ++j) {
+      double d = fabs(A[j][j] - target);
+      if (d < bd) { bd = d; best = j; }
+    }
+    S[S_THETA] = A[best][best];
+    S[S_BETA] = fabs(S[S_NRES] * Q[k - 1][best]);  // Ritz residual estimate |beta_k u_k[last]|
+    S[S_TMP] = (double)best;
+  }
+  __syncwarp();
+  int best = (int)S[S_TMP];
+  for (int j = lane; j < k; j += 32) ritz_coef[j] = Q[j][best];
+}
+
+void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double target, double tol, int kd, int maxiter, bool fixed,
+                   KrylovWork& ws, LocalStats& st) {
+  double* S = ctx->d_scal;
+  auto vec = [&](int i) { return ws.V + (size_t)i * len; };
+  for (int it = 0; it < maxiter; ++it) {
+    kry_nrm2sq(ctx, x, len, S + S_R0N2);
+    kry_scale_to(ctx, x, len, S + S_R0N2, true, vec(0));
+    QTT_CUDA(cudaMemsetAsync(S + OFF_R, 0, sizeof(double) * 64 * 64, ctx->stream));
+    for (int k = 1; k <= kd; ++k) {
+      mv(vec(k - 1), ws.w);
+      st.matvecs++;
+      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
+      kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
+      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
+      kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
+      lanczos_store_col_kernel<<<1, 1, 0, ctx->stream>>>(S, k, 64);
+      check_launch(ctx, "lanczos_store_col");
+      if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k));
+    }
+    {
+      constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
+      static bool configured = false;
+      if (!configured) {
+        QTT_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRitzSmem));
+        configured = true;
+      }
+      ritz_kernel<<<1, 32, kRitzSmem, ctx->stream>>>(S, kd, 64, target, S + OFF_YK);
+    }
+    check_launch(ctx, "ritz");
+    QTT_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
+    kry_axpys(ctx, ws.V, kd, len, S + OFF_YK, x, 1.0);
+    if (fixed) { st.resid = 0.0; return; }
+    double v[8];
+    read_scalars(ctx, 0, 8, v);
+    st.resid = v[S_BETA];
+    st.theta = v[S_THETA];
+    if (v[S_BETA] < tol) { st.converged = 1; return; }
+  }
+}
+
+// ------------------------------------------------------------------ overlap environments <x|b> (ProjMPS)
+// Layouts: Lb [ab][ax], Rb [cb][cx]  (b link slowest).
+void benv_left(Ctx* ctx, const double* Lb, const double* x, const double* bc, double* Lbn, int ax, int cx, int ab, int cb) {
+  size_t mark = ctx->arena.mark();
+  double* T = ctx->arena.alloc((size_t)ab * 2 * cx);
+  GemmDesc g;
+  g.A = Lb; g.B = x; g.C = T;
+  g.M = ab; g.N = 2 * cx; g.K = ax; g.lda = ax; g.ldb = 2 * cx; g.ldc = 2 * cx;
+  gemm(ctx, g);
+  GemmDesc h;
+  h.A = bc; h.B = T; h.C = Lbn; h.transA = true;
+  h.M = cb; h.N = cx; h.K = 2 * ab; h.lda = cb; h.ldb = cx; h.ldc = cx;
+  gemm(ctx, h);
+  ctx->arena.release(mark);
+}
+
+void benv_right(Ctx* ctx, const double* Rb, const double* x, const double* bc, double* Rbn, int ax, int cx, int ab, int cb) {
+  size_t mark = ctx->arena.mark();
+  double* T = ctx->arena.alloc((size_t)ab * 2 * cx);
+  GemmDesc g;
+  g.A = bc; g.B = Rb; g.C = T;
+  g.M = 2 * ab; g.N = cx; g.K = cb; g.lda = cb; g.ldb = cx; g.ldc = cx;
+  gemm(ctx, g);
+  GemmDesc h;
+  h.A = T; h.B = x; h.C = Rbn; h.transB = true;
+  h.M = ab; h.N = ax; h.K = 2 * cx; h.lda = 2 * cx; h.ldb = 2 * cx; h.ldc = ax;
+  gemm(ctx, h);
+  ctx->arena.release(mark);
+}
+
+// proj(P::ProjMPS), reference src/linsolve.jl:13-22: beff[a][s1 s2 c] = Lb[ab][a] b1[ab][s1][m] b2[m][s2][cb] Rb[cb][c]
+void project_rhs(Ctx* ctx, const double* Lb, const double* b1, const double* b2, const double* Rb, double* beff, int ax, int cx,
+                 int ab, int mb, int cb) {
+  size_t mark = ctx->arena.mark();
+  double* bb = ctx->arena.alloc((size_t)4 * ab * cb);
+  double* T1 = ctx->arena.alloc((size_t)4 * ab * cx);
+  GemmDesc g;
+  g.A = b1; g.B = b2; g.C = bb;
+  g.M = 2 * ab; g.N = 2 * cb; g.K = mb; g.lda = mb; g.ldb = 2 * cb; g.ldc = 2 * cb;
+  gemm(ctx, g);
+  GemmDesc h;
+  h.A = bb; h.B = Rb; h.C = T1;
+  h.M = 4 * ab; h.N = cx; h.K = cb; h.lda = cb; h.ldb = cx; h.ldc = cx;
+  gemm(ctx, h);
+  GemmDesc f;
+  f.A = Lb; f.B = T1; f.C = beff; f.transA = true;
+  f.M = ax; f.N = 4 * cx; f.K = ab; f.lda = ax; f.ldb = 4 * cx; f.ldc = 4 * cx;
+  gemm(ctx, f);
+  ctx->arena.release(mark);
+}
+
+void set_one(Ctx* ctx, DBuf& b) {
+  dbuf_reserve(b, 2);
+  set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(b.p, 1, 1.0);
+  check_launch(ctx, "set_one");
+}
+
+double matvec_flops(double chil, double chir, double wl, double wm, double wr) {
+  const double d = 2.0;
+  return 2.0 * (chil * (wl * chil) * (d * d * chir) + (wl * d) * (chil * d * chir) * (wm * d) + (wm * d) * (chil * d * chir) * (wr * d) +
+                (wr * chir) * (chil * d * d) * chir);
+}
+
+struct PhaseTimer {
+  Ctx* ctx;
+  double* acc;
+  bool on;
+  PhaseTimer(Ctx* c, double* a) : ctx(c), acc(a), on(c->profiling && a) {
+    if (on) cudaEventRecord(ctx->ev0, ctx->stream);
+  }
+  ~PhaseTimer() {
+    if (on) {
+      cudaEventRecord(ctx->ev1, ctx->stream);
+      cudaEventSynchronize(ctx->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      *acc += ms;
+    }
+  }
+};
+
+}  // namespace
+
+// Bring x into right-orthonormal form (orthogonality centre at site 1): `orthogonalize!(psi, 1)` of the tdvp driver.
+// Each step is an un-truncated row-space factorisation (one-sided Jacobi) of x[j] viewed as (chi_l) x (2 chi_r).
+void right_orthonormalize(Ctx* ctx, Mps& x) {
+  for (int j = x.n - 1; j >= 1; --j) {
+    const int a = (int)x.chi[j], c = (int)x.chi[j + 1], ap = (int)x.chi[j - 1];
+    size_t need = ((size_t)4 * a * 2 * c + (size_t)2 * ap * a + 4096) * sizeof(double) * 2;
+    ctx->ensure_arena(need);
+    size_t mark = ctx->arena.mark();
+    RowSvd r = svd_rows(ctx, x.core[j].p, a, 2 * c, 0.0, 0, 1, nullptr, 0);
+    const int k = r.k;
+    double* Rf = ctx->arena.alloc((size_t)a * k);
+    GemmDesc g;
+    g.A = x.core[j].p; g.B = r.Wn; g.C = Rf; g.transB = true;
+    g.M = a; g.N = k; g.K = 2 * c; g.lda = 2 * c; g.ldb = 2 * c; g.ldc = k;
+    gemm(ctx, g);
+    double* Xn = ctx->arena.alloc((size_t)2 * ap * k);
+    GemmDesc h;
+    h.A = x.core[j - 1].p; h.B = Rf; h.C = Xn;
+    h.M = 2 * ap; h.N = k; h.K = a; h.lda = a; h.ldb = k; h.ldc = k;
+    gemm(ctx, h);
+    QTT_CUDA(cudaMemcpyAsync(x.core[j].p, r.Wn, sizeof(double) * (size_t)k * 2 * c, cudaMemcpyDeviceToDevice, ctx->stream));
+    QTT_CUDA(cudaMemcpyAsync(x.core[j - 1].p, Xn, sizeof(double) * (size_t)2 * ap * k, cudaMemcpyDeviceToDevice, ctx->stream));
+    x.chi[j] = k;
+    ctx->arena.release(mark);
+  }
+}
+
+// solver_kind: QTT_SOLVER_GMRES needs b; the eigen solvers ignore it.
+void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_sweep_params& P, qtt_sweep_info* infos) {
+  const int n = A.n;
+  QTT_REQUIRE(n >= 2, "need at least 2 sites");
+  QTT_REQUIRE(x.n == n, "MPS length %d != MPO length %d", x.n, n);
+  QTT_REQUIRE(A.dtype == QTT_F64 && x.dtype == QTT_F64 && (!b || b->dtype == QTT_F64),
+              "sweep engine: only Float64 chains are supported in this build");
+  QTT_REQUIRE(A.w[0] == 1 && A.w[n] == 1 && x.chi[0] == 1 && x.chi[n] == 1, "boundary bond dimensions must be 1");
+  if (b) QTT_REQUIRE(b->n == n && b->chi[0] == 1 && b->chi[n] == 1, "rhs MPS shape mismatch");
+  QTT_REQUIRE(P.nsweeps >= 0, "nsweeps < 0");
+  const bool fixed = P.fixed_matvecs > 0;
+  const int kd = fixed ? P.fixed_matvecs : P.krylovdim;
+  QTT_REQUIRE(kd >= 1 && kd <= KD_MAX, "krylovdim must be in [1, %d]", KD_MAX);
+  const int maxiter = P.maxiter > 0 ? P.maxiter : 1;
+  const bool is_lin = (P.solver == QTT_SOLVER_GMRES);
+  QTT_REQUIRE(is_lin || P.solver == QTT_SOLVER_LANCZOS, "solver kind %d not available in this build", P.solver);
+  QTT_REQUIRE(!is_lin || b, "linsolve needs a right-hand side");
+
+  if (!P.x0_canonical) right_orthonormalize(ctx, x);
+
+  std::vector<DBuf> LA(n + 1), RA(n + 1), LB(n + 1), RB(n + 1);
+  auto cleanup = [&]() {
+    for (auto* v : {&LA, &RA, &LB, &RB})
+      for (auto& d : *v) dbuf_free(d);
+  };
+  try {
+    set_one(ctx, LA[0]);
+    set_one(ctx, RA[n]);
+    if (b) { set_one(ctx, LB[0]); set_one(ctx, RB[n]); }
+    int wmax = 1;
+    for (int j = 0; j <= n; ++j) wmax = wmax > (int)A.w[j] ? wmax : (int)A.w[j];
+
+    auto update_right = [&](int j) {  // RA[j] from RA[j+1] and site j
+      const int a = (int)x.chi[j], c = (int)x.chi[j + 1], w = (int)A.w[j], w2 = (int)A.w[j + 1];
+      ctx->ensure_arena((env_scratch(a, c, w, w2) + 4096) * sizeof(double) + ((size_t)8 * a * c + 4096) * sizeof(double));
+      size_t mark = ctx->arena.mark();
+      double* scr = ctx->arena.alloc(env_scratch(a, c, w, w2));
+      dbuf_reserve(RA[j], (size_t)w * a * a);
+      env_right(ctx, RA[j + 1].p, x.core[j].p, A.core[j].p, x.core[j].p, RA[j].p, a, c, a, c, w, w2, scr);
+      ctx->arena.release(mark);
+      if (b) {
+        const int ab = (int)b->chi[j], cb = (int)b->chi[j + 1];
+        dbuf_reserve(RB[j], (size_t)ab * a);
+        benv_right(ctx, RB[j + 1].p, x.core[j].p, b->core[j].p, RB[j].p, a, c, ab, cb);
+      }
+    };
+    auto update_left = [&](int j) {  // LA[j+1] from LA[j] and site j
+      const int a = (int)x.chi[j], c = (int)x.chi[j + 1], w = (int)A.w[j], w2 = (int)A.w[j + 1];
+      ctx->ensure_arena((env_scratch(a, c, w, w2) + 4096) * sizeof(double) + ((size_t)8 * a * c + 4096) * sizeof(double));
+      size_t mark = ctx->arena.mark();
+      double* scr = ctx->arena.alloc(env_scratch(a, c, w, w2));
+      dbuf_reserve(LA[j + 1], (size_t)w2 * c * c);
+      env_left(ctx, LA[j].p, x.core[j].p, A.core[j].p, x.core[j].p, LA[j + 1].p, a, c, a, c, w, w2, scr);
+      ctx->arena.release(mark);
+      if (b) {
+        const int ab = (int)b->chi[j], cb = (int)b->chi[j + 1];
+        dbuf_reserve(LB[j + 1], (size_t)cb * c);
+        benv_left(ctx, LB[j].p, x.core[j].p, b->core[j].p, LB[j + 1].p, a, c, ab, cb);
+      }
+    };
+
+    for (int j = n - 1; j >= 2; --j) update_right(j);
+
+    for (int sw = 0; sw < P.nsweeps; ++sw) {
+      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+      auto t0 = std::chrono::steady_clock::now();
+      qtt_sweep_info info;
+      memset(&info, 0, sizeof(info));
+      const int maxdim = P.maxdim ? P.maxdim[sw] : 0;
+      const int mindim = P.mindim ? P.mindim[sw] : 1;
+      const double cutoff = P.cutoff ? P.cutoff[sw] : 1e-16;
+      for (int dir = 0; dir < 2; ++dir) {
+        for (int step = 0; step < n - 1; ++step) {
+          const int j = dir == 0 ? step : (n - 2 - step);
+          const int chil = (int)x.chi[j], chim = (int)x.chi[j + 1], chir = (int)x.chi[j + 2];
+          const int wl = (int)A.w[j], wm = (int)A.w[j + 1], wr = (int)A.w[j + 2];
+          const size_t len = (size_t)4 * chil * chir;
+          size_t need = (len * (size_t)(kd + 1 + 12) + matvec2_scratch(chil, chir, wl, wr) + (size_t)16 * wl * wr + 65536) * sizeof(double);
+          need += (size_t)256 * (kd + 24);
+          ctx->ensure_arena(need);
+          size_t mark = ctx->arena.mark();
+          double* phi = ctx->arena.alloc(len);
+          double* W12 = ctx->arena.alloc((size_t)16 * wl * wr);
+          double* mvscr = ctx->arena.alloc(matvec2_scratch(chil, chir, wl, wr));
+          KrylovWork ws;
+          ws.V = ctx->arena.alloc(len * (size_t)(kd + 1));
+          ws.w = ctx->arena.alloc(len);
+          ws.r = ctx->arena.alloc(len);
+          {
+            GemmDesc g;  // phi[(a s1)][(s2 c)] = x[j] . x[j+1]
+            g.A = x.core[j].p; g.B = x.core[j + 1].p; g.C = phi;
+            g.M = 2 * chil; g.N = 2 * chir; g.K = chim; g.lda = chim; g.ldb = 2 * chir; g.ldc = 2 * chir;
+            gemm(ctx, g);
+          }
+          build_w12(ctx, A.core[j].p, A.core[j + 1].p, W12, wl, wm, wr);
+          const double* Lp = LA[j].p;
+          const double* Rp = RA[j + 2].p;
+          MatvecFn mv = [&](const double* in, double* out) { matvec2(ctx, Lp, W12, Rp, in, out, chil, chir, wl, wr, mvscr); };
+          LocalStats st;
+          {
+            PhaseTimer pt(ctx, &info.t_krylov);
+            if (is_lin) {
+              double* beff = ctx->arena.alloc(len);
+              project_rhs(ctx, LB[j].p, b->core[j].p, b->core[j + 1].p, RB[j + 2].p, beff, chil, chir, (int)b->chi[j], (int)b->chi[j + 1],
+                          (int)b->chi[j + 2]);
+              gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kd, maxiter, fixed, ws, st);
+            } else {
+              lanczos_local(ctx, mv, phi, len, P.target, P.tol, kd, maxiter, fixed, ws, st);
+              info.energy = st.theta;
+            }
+          }
+          if (fixed && is_lin)
+            QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 70, ctx->d_scal + S_BETA, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+          info.matvecs += st.matvecs;
+          info.flops_matvec += (double)st.matvecs * matvec_flops(chil, chir, wl, wm, wr);
+          if (st.resid > info.solver_resid) info.solver_resid = st.resid;
+          if (P.normalize) {
+            kry_nrm2sq(ctx, phi, len, ctx->d_scal + S_TMP);
+            long nb = (long)((len + 255) / 256);
+            if (nb > 4L * ctx->sms) nb = 4L * ctx->sms;
+            scale_inplace_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(phi, len, ctx->d_scal + S_TMP);
+            check_launch(ctx, "scale_inplace");
+          }
+          int kcap = 2 * chil < 2 * chir ? 2 * chil : 2 * chir;
+          if (maxdim > 0 && maxdim < kcap) kcap = maxdim;
+          dbuf_reserve(x.core[j], (size_t)2 * chil * kcap);
+          dbuf_reserve(x.core[j + 1], (size_t)2 * chir * kcap);
+          SplitResult sr;
+          {
+            PhaseTimer pt(ctx, &info.t_svd);
+            sr = split2(ctx, phi, chil, chir, dir, cutoff, maxdim, mindim, x.core[j].p, x.core[j + 1].p, nullptr, P.svd_max_sweeps);
+          }
+          if (fixed && is_lin && ctx->h_scal[70] > info.solver_resid) info.solver_resid = ctx->h_scal[70];  // split2 synchronised
+          x.chi[j + 1] = sr.rank;
+          if (sr.truncerr > info.maxtruncerr) info.maxtruncerr = sr.truncerr;
+          if (sr.sweeps > info.svd_sweeps_max) info.svd_sweeps_max = sr.sweeps;
+          ctx->arena.release(mark);
+          {
+            PhaseTimer pt(ctx, &info.t_env);
+            // the environment past the turning point is never used (position! would not build it either)
+            if (dir == 0 && j < n - 2) update_left(j);
+            else if (dir == 1 && j > 0) update_right(j + 1);
+          }
+        }
+      }
+      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+      info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      int mld = 1;
+      for (int j = 1; j < n; ++j) mld = mld > (int)x.chi[j] ? mld : (int)x.chi[j];
+      info.maxlinkdim = mld;
+      if (P.outputlevel >= 1) {
+        printf("After sweep %d: maxlinkdim=%d maxerr=%.2E time=%.3f matvecs=%lld\n", sw + 1, mld, info.maxtruncerr, info.seconds,
+               (long long)info.matvecs);
+        fflush(stdout);
+      }
+      if (infos) infos[sw] = info;
+    }
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
+}  // namespace qtt
