@@ -164,7 +164,8 @@ void kry_axpys(Ctx* ctx, const double* V, int nvec, size_t len, const double* h,
 // w += sign * V h and, if nrm2sq_out != null, *nrm2sq_out = ||w_new||^2 (device scalar)
 void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign, double* nrm2sq_out);
 void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out /* device scalar */);
-void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out);
+void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out,
+                  const double* done_dev = nullptr);
 void kry_axpby(Ctx* ctx, size_t len, double a, const double* x, double b, const double* y, double c, const double* z, double* out);
 
 // ------------------------------------------------------------------ SVD split (svd_jacobi.cu)

@@ -125,10 +125,13 @@ __global__ void __launch_bounds__(KT) axpys_kernel(const double* __restrict__ V,
 
 // out[e] = w[e] / d  with d = *denom (or sqrt(*denom))
 __global__ void __launch_bounds__(KT) scale_to_kernel(const double* __restrict__ w, size_t len, const double* __restrict__ denom,
-                                                      int sqrt_denom, double* __restrict__ out) {
+                                                      int sqrt_denom, double* __restrict__ out, const double* __restrict__ done) {
   double d = *denom;
   if (sqrt_denom) d = sqrt(d);
-  const double inv = d != 0.0 ? 1.0 / d : 0.0;
+  // once the Krylov space is exhausted / converged (device flag), later basis vectors are written as zeros so that
+  // run-ahead iterations stay finite and contribute nothing
+  const bool dead = (done != nullptr && *done != 0.0);
+  const double inv = (d != 0.0 && !dead) ? 1.0 / d : 0.0;
   for (size_t e = (size_t)blockIdx.x * KT + threadIdx.x; e < len; e += (size_t)gridDim.x * KT) out[e] = w[e] * inv;
 }
 
@@ -202,9 +205,9 @@ void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out) {
   check_launch(ctx, "kry_nrm2sq");
 }
 
-void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out) {
+void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out, const double* done_dev) {
   unsigned g = grid_for(ctx, len, KT);
-  scale_to_kernel<<<g, KT, 0, ctx->stream>>>(w, len, denom_dev, sqrt_denom ? 1 : 0, out);
+  scale_to_kernel<<<g, KT, 0, ctx->stream>>>(w, len, denom_dev, sqrt_denom ? 1 : 0, out, done_dev);
   check_launch(ctx, "kry_scale_to");
 }
 

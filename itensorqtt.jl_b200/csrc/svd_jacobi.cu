@@ -49,6 +49,7 @@ struct JacobiArgs {
   int q, p, ld;
   int max_sweeps;
   double tol;
+  double zero_tol2;  // rows with |z|^2 <= zero_tol2 * |Z|_F^2 are numerically zero: never rotated, sigma^2 reported as 0
   unsigned* sync;  // [0] barrier counter, [1] spare, [2 + s] rotation count of sweep s
   double* sig2;    // [q] out: squared singular values, descending
   int* perm;       // [q] out: row index of the i-th largest
@@ -70,7 +71,8 @@ __device__ __forceinline__ void rotation(double alpha, double beta, double gamma
 
 // register-resident pair rotation: NCH double2 chunks per lane per row (covers p <= 128 * NCH / 2 ... i.e. 64*NCH columns)
 template <int NCH>
-__device__ __forceinline__ bool rotate_pair_reg(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, int lane) {
+__device__ __forceinline__ bool rotate_pair_reg(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, double thr,
+                                                int lane) {
   double2 za[NCH], zb[NCH];
   double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
@@ -90,6 +92,7 @@ __device__ __forceinline__ bool rotate_pair_reg(double* __restrict__ ra, double*
   alpha = warp_sum(alpha);
   beta = warp_sum(beta);
   gamma = warp_sum(gamma);
+  if (!(alpha > thr) || !(beta > thr)) return false;
   double lim = sqrt(alpha) * sqrt(beta);
   if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
   double c, s;
@@ -108,7 +111,8 @@ __device__ __forceinline__ bool rotate_pair_reg(double* __restrict__ ra, double*
 }
 
 // generic two-pass version for long rows
-__device__ __forceinline__ bool rotate_pair_mem(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, int lane) {
+__device__ __forceinline__ bool rotate_pair_mem(double* __restrict__ ra, double* __restrict__ rb, int ld, double tol, double thr,
+                                                int lane) {
   double alpha = 0.0, beta = 0.0, gamma = 0.0;
   for (int col = 2 * lane; col < ld; col += 64) {
     double2 a = __ldcg(reinterpret_cast<const double2*>(ra + col));
@@ -120,6 +124,7 @@ __device__ __forceinline__ bool rotate_pair_mem(double* __restrict__ ra, double*
   alpha = warp_sum(alpha);
   beta = warp_sum(beta);
   gamma = warp_sum(gamma);
+  if (!(alpha > thr) || !(beta > thr)) return false;
   double lim = sqrt(alpha) * sqrt(beta);
   if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
   double c, s;
@@ -144,6 +149,25 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
   unsigned target = 0;
   int sweeps = 0;
   int converged = (a.q < 2) ? 1 : 0;
+  // |Z|_F^2 (invariant under the rotations) sets the scale below which a row is numerically zero.  Without this a
+  // rank-deficient Z (more rows than the row space has dimensions) never converges: the surplus rows are rounding
+  // noise that keeps being re-orthogonalised at ever smaller scales.
+  for (int i = gw; i < a.q; i += GW) {
+    const double* ri = a.Z + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ld; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  double F2 = 0.0;
+  for (int j = lane; j < a.q; j += 32) F2 += __ldcg(a.norms + j);
+  F2 = warp_sum(F2);
+  const double thr = a.zero_tol2 * F2;
+  grid_sync(a.sync, target);  // norms[] is rewritten after the sweeps
   for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
     bool rotated = false;
     for (int r = 0; r < rounds; ++r) {
@@ -165,8 +189,8 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
         double* ra = a.Z + (size_t)ia * a.ld;
         double* rb = a.Z + (size_t)ib * a.ld;
         bool rot;
-        if constexpr (NCH > 0) rot = rotate_pair_reg<NCH>(ra, rb, a.ld, a.tol, lane);
-        else rot = rotate_pair_mem(ra, rb, a.ld, a.tol, lane);
+        if constexpr (NCH > 0) rot = rotate_pair_reg<NCH>(ra, rb, a.ld, a.tol, thr, lane);
+        else rot = rotate_pair_mem(ra, rb, a.ld, a.tol, thr, lane);
         rotated |= rot;
       }
       grid_sync(a.sync, target);
@@ -185,7 +209,7 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
       acc += v.x * v.x + v.y * v.y;
     }
     acc = warp_sum(acc);
-    if (lane == 0) __stcg(a.norms + i, acc);
+    if (lane == 0) __stcg(a.norms + i, acc > thr ? acc : 0.0);
   }
   grid_sync(a.sync, target);
   // rank sort, descending, ties by index (stable)
@@ -281,6 +305,7 @@ RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxd
   a.Z = Z; a.q = q; a.p = p; a.ld = ld;
   a.max_sweeps = max_sweeps;
   a.tol = sqrt((double)p) * 1.1102230246251565e-16;
+  a.zero_tol2 = (8.0 * a.tol) * (8.0 * a.tol);
   a.sync = ctx->d_sync + 8;
   a.sig2 = sig2; a.perm = perm; a.norms = norms; a.info = info; a.derr = derr;
   a.cutoff = cutoff;

@@ -52,10 +52,14 @@ __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, doub
   double* gc = S + OFF_GC;
   double* gs = S + OFF_GS;
   if (k == 1) y[0] = sqrt(S[S_R0N2]);
+  double hn2 = nres * nres;
   for (int i = 0; i < k; ++i) {
     double h = S[OFF_H1 + i] + S[OFF_H2 + i];
+    hn2 += h * h;
     Rm[i * ld + (k - 1)] = (i == k - 1) ? (a0 + a1 * h) : (a1 * h);
   }
+  // Krylov space exhausted (invariant subspace): the next basis vector would be rounding noise
+  const bool breakdown = !(nres > 1e-13 * sqrt(hn2));
   for (int i = 0; i < k - 1; ++i) {
     double t1 = Rm[i * ld + (k - 1)], t2 = Rm[(i + 1) * ld + (k - 1)];
     Rm[i * ld + (k - 1)] = gc[i] * t1 + gs[i] * t2;
@@ -72,7 +76,7 @@ __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, doub
   double beta = fabs(y[k]);
   S[S_BETA] = beta;
   S[S_K] = (double)k;
-  if (!(beta > tol)) S[S_DONE] = 1.0;
+  if (!(beta > tol) || breakdown) S[S_DONE] = 1.0;
   if (hstat) {
     hstat[H_K] = (double)k;
     hstat[H_BETA] = beta;
@@ -82,7 +86,11 @@ __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, doub
 }
 
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
-__global__ void gmres_solve_kernel(double* S, int k, int ld) {
+__global__ void gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) {
+  // k >= 0: use k columns.  k < 0: use the device-side step count S_K and zero-fill yk up to kd = -k.
+  int k = k_or_neg_kd;
+  int kd = 0;
+  if (k < 0) { kd = -k; k = (int)S[S_K]; }
   double* Rm = S + OFF_R;
   double* y = S + OFF_Y;
   double* gc = S + OFF_GC;
@@ -103,6 +111,7 @@ __global__ void gmres_solve_kernel(double* S, int k, int ld) {
   }
   for (int i = 0; i <= k; ++i) coef[i] *= y[k];
   S[S_R0N2] = y[k] * y[k];
+  for (int i = k; i < kd; ++i) yk[i] = 0.0;
 }
 
 __global__ void set_scalars_kernel(double* p, int n, double v) {
@@ -173,7 +182,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
       kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
       gmres_update_kernel<<<1, 1, 0, ctx->stream>>>(S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
       check_launch(ctx, "gmres_update");
-      kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k));
+      kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
       if (!fixed && hstat[H_DONE] != 0.0) break;
     }
     int kfin = kd;
@@ -184,7 +193,9 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
       beta = v[S_BETA];
       st.resid = beta;
     }
-    gmres_solve_kernel<<<1, 1, 0, ctx->stream>>>(S, kfin, 64);
+    // fixed mode: the device-side step count (S_K < kd after an early breakdown) is used by the kernel itself; the
+    // coefficients beyond it are zero and the corresponding basis vectors were written as zeros.
+    gmres_solve_kernel<<<1, 1, 0, ctx->stream>>>(S, fixed ? -kd : kfin, 64);
     check_launch(ctx, "gmres_solve");
     kry_axpys(ctx, ws.V, kfin, len, S + OFF_YK, x, 1.0);
     if (fixed) return;
@@ -211,16 +222,23 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
 // single-warp cyclic Jacobi kernel; the Ritz vector nearest `target` is assembled with one multi-axpy.
 __global__ void lanczos_store_col_kernel(double* S, int k, int ld) {
   // column k-1 of the projected matrix from the CGS2 coefficients; subdiagonal = residual norm
+  if (S[S_DONE] != 0.0) return;
   double* T = S + OFF_R;
+  double nres = sqrt(S[S_NRES2]);
+  double hn2 = nres * nres;
   for (int i = 0; i < k; ++i) {
     double h = S[OFF_H1 + i] + S[OFF_H2 + i];
+    hn2 += h * h;
     T[i * ld + (k - 1)] = h;
     T[(k - 1) * ld + i] = h;
   }
-  S[S_NRES] = sqrt(S[S_NRES2]);
+  S[S_NRES] = nres;
+  S[S_K] = (double)k;
+  if (!(nres > 1e-13 * sqrt(hn2))) S[S_DONE] = 1.0;  // invariant subspace: stop expanding (KrylovKit: normres <= tol)
 }
 
-__global__ void __launch_bounds__(32) ritz_kernel(double* S, int k, int ld, double target, double* ritz_coef) {
+__global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, double target, double* ritz_coef) {
+  const int k = (int)S[S_K];
   // cyclic Jacobi eigen-decomposition of the k x k symmetric T in shared memory (k <= 62); lane-parallel row/col updates
   extern __shared__ double ritz_sm[];
   double(*A)[65] = reinterpret_cast<double(*)[65]>(ritz_sm);
@@ -286,7 +304,7 @@ __global__ void __launch_bounds__(32) ritz_kernel(double* S, int k, int ld, doub
   }
   __syncwarp();
   int best = (int)S[S_TMP];
-  for (int j = lane; j < k; j += 32) ritz_coef[j] = Q[j][best];
+  for (int j = lane; j < kd; j += 32) ritz_coef[j] = j < k ? Q[j][best] : 0.0;
 }
 
 void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double target, double tol, int kd, int maxiter, bool fixed,
@@ -295,6 +313,8 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
   auto vec = [&](int i) { return ws.V + (size_t)i * len; };
   for (int it = 0; it < maxiter; ++it) {
     kry_nrm2sq(ctx, x, len, S + S_R0N2);
+    set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
+    check_launch(ctx, "set_scalars");
     kry_scale_to(ctx, x, len, S + S_R0N2, true, vec(0));
     QTT_CUDA(cudaMemsetAsync(S + OFF_R, 0, sizeof(double) * 64 * 64, ctx->stream));
     for (int k = 1; k <= kd; ++k) {
@@ -306,7 +326,7 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
       kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
       lanczos_store_col_kernel<<<1, 1, 0, ctx->stream>>>(S, k, 64);
       check_launch(ctx, "lanczos_store_col");
-      if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k));
+      if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
     }
     {
       constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
@@ -538,15 +558,16 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const double* Rp = RA[j + 2].p;
           MatvecFn mv = [&](const double* in, double* out) { matvec2(ctx, Lp, W12, Rp, in, out, chil, chir, wl, wr, mvscr); };
           LocalStats st;
+          const int kdl = (size_t)kd < len ? kd : (int)len;  // a Krylov space cannot exceed the local dimension
           {
             PhaseTimer pt(ctx, &info.t_krylov);
             if (is_lin) {
               double* beff = ctx->arena.alloc(len);
               project_rhs(ctx, LB[j].p, b->core[j].p, b->core[j + 1].p, RB[j + 2].p, beff, chil, chir, (int)b->chi[j], (int)b->chi[j + 1],
                           (int)b->chi[j + 2]);
-              gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kd, maxiter, fixed, ws, st);
+              gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws, st);
             } else {
-              lanczos_local(ctx, mv, phi, len, P.target, P.tol, kd, maxiter, fixed, ws, st);
+              lanczos_local(ctx, mv, phi, len, P.target, P.tol, kdl, maxiter, fixed, ws, st);
               info.energy = st.theta;
             }
           }

@@ -118,7 +118,8 @@ def gmres_krylovkit(matvec, b, x0, a0=0.0, a1=1.0, tol=1e-12, krylovdim=30, maxi
     operator is applied 1 + fixed_matvecs times.
     Returns (x, info) with info = dict(converged, normres, numiter, numops)."""
     if fixed_matvecs is not None:
-        krylovdim, maxiter, tol = int(fixed_matvecs), 1, -1.0
+        # a Krylov space cannot exceed the dimension of the local problem
+        krylovdim, maxiter, tol = int(min(fixed_matvecs, b.size)), 1, -1.0
     shape = b.shape
     bv = b.reshape(-1)
     x = x0.reshape(-1).copy()
@@ -231,6 +232,8 @@ def eigsolve_krylovkit(matvec, x0, which="LM", target=None, tol=1e-12, krylovdim
     numiter = 0
     beta = 0.0
     w = None
+    krylovdim = int(min(krylovdim, v.size))
+    invariant = False
     while True:
         # expand until krylovdim
         while k < krylovdim:
@@ -244,7 +247,9 @@ def eigsolve_krylovkit(matvec, x0, which="LM", target=None, tol=1e-12, krylovdim
                     sdot = np.vdot(V[i], w); w = w - sdot * V[i]; Hm[i, k] += sdot
             beta = np.linalg.norm(w)
             k += 1
-            if beta < 1e-300:
+            # invariant subspace (KrylovKit stops expanding when normres <= tol); also guards w / beta
+            if beta <= max(tol, 1e-13 * np.linalg.norm(Hm[:k, k - 1])):
+                invariant = True
                 break
             if k < krylovdim:
                 V.append(w / beta); Hm[k, k - 1] = beta
@@ -258,7 +263,7 @@ def eigsolve_krylovkit(matvec, x0, which="LM", target=None, tol=1e-12, krylovdim
         converged = 0
         while converged < k and abs(f[converged]) < tol:
             converged += 1
-        if converged >= 1 or numiter >= maxiter or beta < 1e-300:
+        if converged >= 1 or numiter >= maxiter or invariant:
             vec = sum(U[i, 0] * V[i] for i in range(k))
             return D[0], vec.reshape(shape), dict(converged=converged, normres=abs(f[0]), numiter=numiter, numops=numops)
         keep = (3 * krylovdim + 2 * converged) // 5
