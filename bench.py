@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200-native QTT sweep engine (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one two-site linsolve sweep (forward + reverse half-sweep, 2(n-1) bond updates) of the Helmholtz
+workload of BASELINE.json configs[1]: n = 30 bits, chi = 256 (maxdim = mindim = 256, cutoff = 0), second-order
+Laplacian MPO (w = 3) with the shift passed as a0 = -lambda, fixed-work local solver (one GMRES cycle of 30
+Arnoldi steps = 31 effective-operator applications per bond; SURVEY.md section 7 explains why a fixed Krylov budget
+is needed for a well-defined sweeps/s).  Inputs are synthetic (numpy default_rng start vector, analytic operands).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job sweeps/s with the chains already resident in HBM, timed on the
+device (CUDA events recorded by the library on its own stream), max over ranks; `e2e` = the same through the public
+API with HOST buffers (upload + sweep + download inside the timed region); `roofline` = the local matvec against the
+measured FP64 DMMA peak; `cpu_baseline` = the numpy/OpenBLAS oracle port on the host cores (bounded sample).
+At N > 1 every rank solves an independent instance (wavenumber k_i): weak scaling, NCCL only gathers residuals.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BITS, CHI, NK, KRYLOV = 30, 256, 18, 30
+FP64_DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200: tools/fp64_peak.cu -> profiles/r01_fp64_peak_dmma_dfma.txt
+METRIC = "QTT linsolve sweeps/s (n=30 bits, chi=256); local-matvec FP64 TFLOP/s vs peak"
+
+
+def bond_dims(n, chi):
+    return [1] + [int(min(chi, 2 ** j, 2 ** (n - j))) for j in range(1, n)] + [1]
+
+
+def sweep_matvec_flops(n, chi, w, matvecs_per_bond):
+    """Algorithmic FP64 flops of the matvecs of one sweep (SURVEY.md 8d formula with the actual edge bond dims)."""
+    from itensorqtt_jl_b200 import matvec2_flops
+    d = bond_dims(n, chi)
+    ws = [1] + [w] * (n - 1) + [1]
+    per_bond = []
+    for j in range(n - 1):
+        ln = 4 * d[j] * d[j + 2]
+        mv = 1 + min(matvecs_per_bond, ln)
+        per_bond.append(mv * matvec2_flops(d[j], d[j + 2], ws[j], ws[j + 1], ws[j + 2]))
+    return 2.0 * sum(per_bond), per_bond
+
+
+def workload(rank=0, n=N_BITS, chi=CHI, nk=NK):
+    """Operands as host cores (package builders; the oracle is not involved)."""
+    import itensorqtt_jl_b200 as q
+    A = q.laplacian_mpo(n, 1.0)
+    # independent instances at N > 1: wavenumber k_i = 2 pi (2^nk + rank)  (SURVEY.md 8d cfg 5 recipe)
+    lam = -((2 * np.pi * (2.0 ** nk + rank) / 2.0 ** n) ** 2)
+    b = q.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
+    x0 = q.random_mps(n, chi, 2 + rank)
+    return A, b, x0, lam
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0.5 * max(mx or [1])] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_fortran_copy(cores):
+    """Host cores re-homed in PINNED memory, column-major (what the C ABI borrows)."""
+    import torch
+    out = []
+    for c in cores:
+        t = torch.empty(c.size, dtype=torch.float64).pin_memory()
+        a = np.ndarray(c.shape, dtype=np.float64, buffer=t.numpy().data, order="F")
+        a[...] = c
+        a._pin = t  # keep the pinned tensor alive
+        out.append(a)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import itensorqtt_jl_b200 as q
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (libqtt_b200 has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, chi = args.n, args.chi
+    A, b, x0, lam = workload(rank, n, chi, args.nk)
+    ctx = q.default_context(local)
+    dA, db = q.DeviceMPO(A, ctx), q.DeviceMPS(b, ctx)
+    dx = q.DeviceMPS(x0, ctx)
+    kw = dict(nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov, ctx=ctx, return_info=True, on_device=True)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x, canonical):
+        flush.zero_()           # evict L2 between timed steps
+        torch.cuda.synchronize()
+        y, info = q.linsolve(dA, db, x, -lam, 1.0, x0_canonical=canonical, **kw)
+        return y, info[0]
+
+    x = dx
+    for i in range(args.warmup):
+        x, info = step(x, canonical=True)   # random_mps() is right-orthonormal by construction
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    dev_ms, infos = 0.0, []
+    for i in range(args.steps):
+        x, info = step(x, canonical=True)
+        dev_ms += info["device_ms"]
+        infos.append(info)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    ms_per_step = dev_ms / max(args.steps, 1)
+    # residual of the final state (device-side metric kernel if available, else skipped)
+    t = torch.tensor([ms_per_step, wall, float(infos[-1]["solver_resid"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)     # NCCL over NVLink: residuals / timings only
+        allt = torch.stack(gathered).cpu().numpy()
+    else:
+        allt = t.cpu().numpy()[None]
+    ms_max = float(allt[:, 0].max())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    flops_sweep, _ = sweep_matvec_flops(n, chi, 3, args.krylov)
+    value = world / (ms_max / 1e3)
+    # ---- roofline of the local matvec (dominant work: 2 DMMA GEMM launches + 2 streaming kernels), live CUDA events
+    rng = np.random.default_rng(0)
+    L = rng.standard_normal((chi, 3, chi)); R = rng.standard_normal((chi, 3, chi))
+    W = A[1]
+    v = rng.standard_normal((chi, 2, 2, chi))
+    _, mv_ms = q.matvec2(L, W, W, R, v, reps=200, ctx=ctx)
+    f_mv = q.matvec2_flops(chi, chi, 3, 3, 3)
+    achieved = f_mv / (mv_ms * 1e-3) / 1e12
+    sweep_mv_tflops = infos[-1]["flops_matvec"] / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 (gemm_dmma_kernel x2 + apply_w12 + sum_partials)" % chi,
+                "flops_per_launch": f_mv, "ms_per_launch": mv_ms,
+                "peak_source": "measured FP64 DMMA.8x8x4 issue rate on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak_dmma_dfma.txt); "
+                               "MEASURED_PEAKS.json carries no FP64 entry",
+                "matvec_tflops_inside_sweep_incl_krylov_svd_env": sweep_mv_tflops}
+    # ---- e2e: host buffers -> upload -> one sweep -> download
+    hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x0)
+    e2e_steps = max(1, min(args.steps, 2))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
+                           x0_canonical=True, ctx=ctx, return_info=True)
+    e2e_t = (time.perf_counter() - t0) / e2e_steps
+    h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)
+    d2h = sum(c.nbytes for c in xo)
+    out = {
+        "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]): laplacian_mpo w=3, a0=-lambda (nk=%d), "
+                               "maxdim=mindim=%d, cutoff=0, fixed-work GMRES %d Arnoldi steps/bond" % (n, chi, args.nk, chi, args.krylov),
+                   "bonds_per_sweep": 2 * (n - 1), "matvecs_per_sweep": int(infos[-1]["matvecs"]),
+                   "instances": world, "l2": "256 MB buffer written between timed steps (L2 flush)",
+                   "wall_s_timed_region": wall},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "roofline": roofline,
+        "sweep": {"matvec_flops_per_sweep": flops_sweep, "maxlinkdim": int(infos[-1]["maxlinkdim"]),
+                  "svd_sweeps_max": int(infos[-1]["svd_sweeps_max"]), "solver_resid_max_over_ranks": float(allt[:, 2].max())},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_sample(args, steps=1, warmup=0)
+    print(json.dumps(out))
+    sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample(args, steps, warmup):
+    """The oracle port (numpy tensordot -> OpenBLAS dgemm, LAPACK gesdd, KrylovKit-style GMRES) timed on the host cores
+    on a bounded sample: `m` consecutive full-size forward bond updates of the same workload, extrapolated to a sweep
+    by algorithmic matvec flops.  Used for `cpu_baseline` and for `--impl reference`."""
+    import oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    n, chi = args.n, args.chi
+    A = O.laplacian_mpo(n, 1.0)
+    lam = -((2 * np.pi * (2.0 ** args.nk) / 2.0 ** n) ** 2)
+    b = O.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
+    x0 = O.random_mps(n, chi, 2)
+    d = bond_dims(n, chi)
+    full = [j for j in range(n - 1) if d[j] == chi and d[j + 2] == chi]
+    j0 = full[0] if full else 0
+    m = max(1, min(args.cpu_bonds, len(full) if full else 1))
+    total, per_bond = sweep_matvec_flops(n, chi, 3, args.krylov)
+    weight = total / sum(per_bond[j0:j0 + m])
+    times = []
+    for i in range(warmup + steps):
+        _, rec = O.linsolve(A, b, x0, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
+                            bond_window=(j0, m))
+        times.append(rec[0]["seconds"])  # the bond updates only; the window's environment set-up is not timed
+    t = float(np.mean(times[warmup:]))
+    return {"value": 1.0 / (t * weight), "unit": "sweeps/s", "cores": int(threads), "kind": "port",
+            "sample": "%d consecutive full-size (chi=%d) forward bond updates starting at bond %d (merge, %d matvecs + GMRES, "
+                      "SVD split, environment update) = %.2f s; extrapolated to one sweep by "
+                      "algorithmic matvec flops (x%.1f)" % (m, chi, j0 + 1, args.krylov + 1, t, weight),
+            "seconds_per_sample": t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_sample(args, steps=max(args.steps, 1), warmup=args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "sweeps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_sample"] * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]), CPU oracle port; the Julia reference cannot run "
+                                  "here (no julia toolchain, dependencies not vendored)" % (args.n, args.chi)},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_BITS)
+    ap.add_argument("--chi", type=int, default=CHI)
+    ap.add_argument("--nk", type=int, default=NK)
+    ap.add_argument("--krylov", type=int, default=KRYLOV)
+    ap.add_argument("--cpu-bonds", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,7 @@ typedef struct {
   double flops_matvec;     /* algorithmic FP64 flops of those matvecs (SURVEY.md 8d formula, actual bond dims) */
   double t_matvec, t_env, t_svd, t_krylov; /* CUDA-event milliseconds per phase (0 unless profiling enabled) */
   double energy;           /* eigen solvers: last local Ritz value; linsolve: 0 */
+  double device_ms;        /* CUDA-event time of the sweep on the context's stream */
 } qtt_sweep_info;
 
 /* `linsolve(A::MPO, b::MPS, x0::MPS, a0, a1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter)`

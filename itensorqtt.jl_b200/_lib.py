@@ -33,6 +33,7 @@ class SweepInfo(C.Structure):
         ("maxlinkdim", C.c_int32), ("svd_sweeps_max", C.c_int32), ("maxtruncerr", C.c_double), ("seconds", C.c_double),
         ("solver_resid", C.c_double), ("matvecs", C.c_int64), ("flops_matvec", C.c_double), ("t_matvec", C.c_double),
         ("t_env", C.c_double), ("t_svd", C.c_double), ("t_krylov", C.c_double), ("energy", C.c_double),
+        ("device_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -522,9 +522,13 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
 
     for (int j = n - 1; j >= 2; --j) update_right(j);
 
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;
+    QTT_CUDA(cudaEventCreate(&evs0));
+    QTT_CUDA(cudaEventCreate(&evs1));
     for (int sw = 0; sw < P.nsweeps; ++sw) {
       QTT_CUDA(cudaStreamSynchronize(ctx->stream));
       auto t0 = std::chrono::steady_clock::now();
+      QTT_CUDA(cudaEventRecord(evs0, ctx->stream));
       qtt_sweep_info info;
       memset(&info, 0, sizeof(info));
       const int maxdim = P.maxdim ? P.maxdim[sw] : 0;
@@ -605,8 +609,14 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           }
         }
       }
+      QTT_CUDA(cudaEventRecord(evs1, ctx->stream));
       QTT_CUDA(cudaStreamSynchronize(ctx->stream));
       info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs0, evs1);
+        info.device_ms = ms;
+      }
       int mld = 1;
       for (int j = 1; j < n; ++j) mld = mld > (int)x.chi[j] ? mld : (int)x.chi[j];
       info.maxlinkdim = mld;
@@ -617,6 +627,8 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
       }
       if (infos) infos[sw] = info;
     }
+    cudaEventDestroy(evs0);
+    cudaEventDestroy(evs1);
   } catch (...) {
     cleanup();
     throw;

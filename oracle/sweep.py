@@ -307,7 +307,7 @@ def _per_sweep(v, nsweeps, default):
 
 
 def two_site_sweeps(A, x0, solver, nsweeps, maxdim=None, mindim=1, cutoff=1e-16, b=None, normalize=False,
-                    bra=None, timers=None):
+                    bra=None, timers=None, bond_window=None):
     """`tdvp(solver, P, t=Inf, x0; reverse_step=false, nsite=2, nsweeps, maxdim, mindim, cutoff)`
     (App. B.1): per sweep a forward half-sweep (bonds 1..n-1, ortho "left") then a reverse
     half-sweep (bonds n-1..1, ortho "right"); per bond position!, phi = x[b]*x[b+1],
@@ -316,9 +316,13 @@ def two_site_sweeps(A, x0, solver, nsweeps, maxdim=None, mindim=1, cutoff=1e-16,
     solver(env, phi) -> phi', where env = dict(L, W1, W2, R, Lb, Rb, b1, b2, bond, n).
     `b`  : optional MPS for the ProjMPS overlap environments (ProjMPO_MPS(A, [b])).
     `bra`: optional MPS used as the bra of the operator environments (ProjMPOLinsolve, src/linsolve.jl:175-253).
+    `bond_window=(j0, m)` (bench sampling only): process just the m forward bond updates j0..j0+m-1 of the
+    first half-sweep, starting from x0 brought to orthogonality centre j0 with the environments it needs.
     Returns (x, records)."""
     n = len(A)
     assert len(x0) == n and n >= 2
+    if bond_window is not None:
+        return _window_sweep(A, x0, solver, bond_window, maxdim, mindim, cutoff, b, timers)
     maxdims = _per_sweep(maxdim, nsweeps, None)
     mindims = _per_sweep(mindim, nsweeps, 1)
     cutoffs = _per_sweep(cutoff, nsweeps, 1e-16)
@@ -392,9 +396,51 @@ def two_site_sweeps(A, x0, solver, nsweeps, maxdim=None, mindim=1, cutoff=1e-16,
     return x, records
 
 
+def _window_sweep(A, x0, solver, bond_window, maxdim, mindim, cutoff, b, timers):
+    n = len(A)
+    j0, m = bond_window
+    assert 0 <= j0 and j0 + m <= n - 1
+    md = _per_sweep(maxdim, 1, None)[0]; mn = _per_sweep(mindim, 1, 1)[0]; co = _per_sweep(cutoff, 1, 1e-16)[0]
+    x = orthogonalize(x0, j0)
+    dt = np.result_type(x[0], A[0]) if b is None else np.result_type(x[0], A[0], b[0])
+    LA = [None] * (n + 1); RA = [None] * (n + 1); LB = [None] * (n + 1); RB = [None] * (n + 1)
+    LA[0] = np.ones((1, 1, 1), dtype=dt); RA[n] = np.ones((1, 1, 1), dtype=dt)
+    LB[0] = np.ones((1, 1), dtype=dt); RB[n] = np.ones((1, 1), dtype=dt)
+    for j in range(j0):
+        LA[j + 1] = env_left_update(LA[j], x[j], A[j])
+        if b is not None:
+            LB[j + 1] = benv_left_update(LB[j], x[j], b[j])
+    for j in range(n - 1, j0 + 1, -1):
+        RA[j] = env_right_update(RA[j + 1], x[j], A[j])
+        if b is not None:
+            RB[j] = benv_right_update(RB[j + 1], x[j], b[j])
+    tm = timers if timers is not None else {}
+    for key in ("env", "solver", "svd"):
+        tm.setdefault(key, 0.0)
+    t_start = time.perf_counter()
+    maxerr = 0.0
+    for j in range(j0, j0 + m):
+        phi = np.tensordot(x[j], x[j + 1], axes=([2], [0]))
+        env = dict(L=LA[j], W1=A[j], W2=A[j + 1], R=RA[j + 2], bond=j, n=n,
+                   Lb=LB[j] if b is not None else None, Rb=RB[j + 2] if b is not None else None,
+                   b1=b[j] if b is not None else None, b2=b[j + 1] if b is not None else None, bra1=None, bra2=None)
+        t0 = time.perf_counter(); phi = solver(env, phi); tm["solver"] += time.perf_counter() - t0
+        t0 = time.perf_counter(); Aj, Bj, err, _ = split_two_site(phi, "left", co, md, mn); tm["svd"] += time.perf_counter() - t0
+        maxerr = max(maxerr, err)
+        x[j] = Aj; x[j + 1] = Bj
+        t0 = time.perf_counter()
+        LA[j + 1] = env_left_update(LA[j], x[j], A[j])
+        if b is not None:
+            LB[j + 1] = benv_left_update(LB[j], x[j], b[j])
+        tm["env"] += time.perf_counter() - t0
+    rec = SweepRecord(sweep=1, maxlinkdim=max(c.shape[2] for c in x[:-1]), maxtruncerr=maxerr,
+                      seconds=time.perf_counter() - t_start)
+    return x, [rec]
+
+
 # ------------------------------------------------------------------ front-ends
 def linsolve(A, b, x0, a0=0.0, a1=1.0, nsweeps=1, maxdim=None, mindim=1, cutoff=1e-16, tol=1e-5, krylovdim=20,
-             maxiter=10, ishermitian=False, normalize=False, fixed_matvecs=None, stats=None, timers=None):
+             maxiter=10, ishermitian=False, normalize=False, fixed_matvecs=None, stats=None, timers=None, bond_window=None):
     """`linsolve(A::MPO, b::MPS, x0::MPS, a0, a1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter)`:
     body restated from examples/airy_equation/src/linsolve.jl:24-34 (defaults tol=1e-5,
     krylovdim=20, maxiter=10): ProjMPO_MPS(A, [b]); local solver = KrylovKit GMRES on
@@ -411,7 +457,8 @@ def linsolve(A, b, x0, a0=0.0, a1=1.0, nsweeps=1, maxdim=None, mindim=1, cutoff=
         st["gmres_resid"] = max(st["gmres_resid"], float(info["normres"]))
         return xloc
 
-    return two_site_sweeps(A, x0, solver, nsweeps, maxdim, mindim, cutoff, b=b, normalize=normalize, timers=timers)
+    return two_site_sweeps(A, x0, solver, nsweeps, maxdim, mindim, cutoff, b=b, normalize=normalize, timers=timers,
+                           bond_window=bond_window)
 
 
 def linsolve_pseudoinverse(A, b, x0, a0=0.0, a1=1.0, nsweeps=1, maxdim=None, mindim=1, cutoff=1e-16, **_):

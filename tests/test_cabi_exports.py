@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     import itensorqtt_jl_b200 as q
     # qtt_sweep_params: int32, 3 pointers, int32, 3 doubles, ... (natural alignment, 64-bit)
     assert ctypes.sizeof(q.SweepParams) == 104
-    assert ctypes.sizeof(q.SweepInfo) == 88
+    assert ctypes.sizeof(q.SweepInfo) == 96
 
 
 def test_no_cpu_fallback():
