@@ -106,6 +106,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_PINNED = []
+
+
 def pinned_fortran_copy(cores):
     """Host cores re-homed in PINNED memory, column-major (what the C ABI borrows)."""
     import torch
@@ -114,7 +117,7 @@ def pinned_fortran_copy(cores):
         t = torch.empty(c.size, dtype=torch.float64).pin_memory()
         a = np.ndarray(c.shape, dtype=np.float64, buffer=t.numpy().data, order="F")
         a[...] = c
-        a._pin = t  # keep the pinned tensor alive
+        _PINNED.append(t)  # keep the pinned tensor alive
         out.append(a)
     return out
 

@@ -18,37 +18,57 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// partial[cta][i] = sum over the CTA's elements of V[i][e] * w[e]; last CTA reduces to h[i] (optionally h[i] += ..)
+// partial[cta][i] = sum over the CTA's elements of V[i][e] * w[e] for up to NV vectors at once (accumulators in
+// registers, ONE block-level reduction for all of them); the last CTA to arrive reduces the partials in a fixed order.
+constexpr int NV = 32;
 __global__ void __launch_bounds__(KT) dots_kernel(const double* __restrict__ V, int nvec, size_t len, const double* __restrict__ w,
                                                   double* __restrict__ partial, double* __restrict__ h, unsigned int* counter,
                                                   int accumulate) {
-  __shared__ double red[KT / 32];
+  __shared__ double red[KT / 32][NV + 1];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = 0; i < nvec; ++i) {
-    double acc = 0.0;
-    const double* vi = V + (size_t)i * len;
-    for (size_t base = (size_t)blockIdx.x * CHUNK; base < len; base += (size_t)gridDim.x * CHUNK) {
-      size_t e = base + (size_t)tid * EPT;
-      if (e + EPT <= len && ((len & 1) == 0)) {
-        double2 a0 = *reinterpret_cast<const double2*>(vi + e), a1 = *reinterpret_cast<const double2*>(vi + e + 2);
-        double2 b0 = *reinterpret_cast<const double2*>(w + e), b1 = *reinterpret_cast<const double2*>(w + e + 2);
-        acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
-      } else {
-        for (int k = 0; k < EPT; ++k)
-          if (e + k < len) acc += vi[e + k] * w[e + k];
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  const bool vec_ok = ((len & 1) == 0);
+  for (size_t base = (size_t)blockIdx.x * CHUNK; base < len; base += (size_t)gridDim.x * CHUNK) {
+    size_t e = base + (size_t)tid * EPT;
+    if (e + EPT <= len && vec_ok) {
+      double2 b0 = *reinterpret_cast<const double2*>(w + e), b1 = *reinterpret_cast<const double2*>(w + e + 2);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (i < nvec) {
+          const double* vi = V + (size_t)i * len + e;
+          double2 a0 = *reinterpret_cast<const double2*>(vi), a1 = *reinterpret_cast<const double2*>(vi + 2);
+          acc[i] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
+        }
+      }
+    } else {
+      for (int k = 0; k < EPT; ++k) {
+        if (e + k < len) {
+          double wv = w[e + k];
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (i < nvec) acc[i] += V[(size_t)i * len + e + k] * wv;
+        }
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int k = 0; k < KT / 32; ++k) s += red[k];
-      partial[(size_t)blockIdx.x * nvec + i] = s;
-    }
-    __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nvec) {
+      double v = warp_sum(acc[i]);
+      if (lane == 0) red[warp][i] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < nvec) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < KT / 32; ++k) s += red[k][tid];
+    partial[(size_t)blockIdx.x * nvec + tid] = s;
+  }
+  __syncthreads();
   if (tid == 0) {
     __threadfence();
     unsigned int prev = atomicAdd(counter, 1u);
@@ -57,10 +77,15 @@ __global__ void __launch_bounds__(KT) dots_kernel(const double* __restrict__ V, 
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int i = tid; i < nvec; i += KT) {
+    // nvec * 8 threads: 8 lanes cooperate on each vector's column of partials
+    const int grp = tid >> 3, sub = tid & 7;
+    for (int i = grp; i < nvec; i += KT / 8) {
       double s = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * nvec + i);
-      h[i] = accumulate ? (h[i] + s) : s;
+      for (unsigned int b = sub; b < gridDim.x; b += 8) s += __ldcg(partial + (size_t)b * nvec + i);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (sub == 0) h[i] = accumulate ? (h[i] + s) : s;
     }
     if (tid == 0) *counter = 0;
   }
@@ -168,20 +193,24 @@ double* Ctx::partial(size_t n) {
   return d_partial;
 }
 
+static void dots_impl(Ctx* ctx, const double* V, int nvec, size_t len, const double* w, double* h, int accumulate) {
+  unsigned g = grid_for(ctx, len, CHUNK);
+  for (int i0 = 0; i0 < nvec; i0 += NV) {
+    int nv = nvec - i0 < NV ? nvec - i0 : NV;
+    double* part = ctx->partial((size_t)g * nv);
+    dots_kernel<<<g, KT, 0, ctx->stream>>>(V + (size_t)i0 * len, nv, len, w, part, h + i0, ctx->d_sync + 0, accumulate);
+    check_launch(ctx, "kry_dots");
+  }
+}
+
 void kry_dots(Ctx* ctx, const double* V, int nvec, size_t len, const double* w, double* h) {
   if (nvec <= 0) return;
-  unsigned g = grid_for(ctx, len, CHUNK);
-  double* part = ctx->partial((size_t)g * nvec);
-  dots_kernel<<<g, KT, 0, ctx->stream>>>(V, nvec, len, w, part, h, ctx->d_sync + 0, 0);
-  check_launch(ctx, "kry_dots");
+  dots_impl(ctx, V, nvec, len, w, h, 0);
 }
 
 void kry_dots_acc(Ctx* ctx, const double* V, int nvec, size_t len, const double* w, double* h) {
   if (nvec <= 0) return;
-  unsigned g = grid_for(ctx, len, CHUNK);
-  double* part = ctx->partial((size_t)g * nvec);
-  dots_kernel<<<g, KT, 0, ctx->stream>>>(V, nvec, len, w, part, h, ctx->d_sync + 0, 1);
-  check_launch(ctx, "kry_dots_acc");
+  dots_impl(ctx, V, nvec, len, w, h, 1);
 }
 
 void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign, double* nrm2sq_out) {

@@ -45,6 +45,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 struct JacobiArgs {
+  double* Zi;      // imaginary plane (same layout) or nullptr for real data
+  int eigen_mode;  // 1: the spectrum that is truncated is |row| (eigenvalues of a Hermitian PSD matrix), not |row|^2
   double* Z;       // [q][ld] row-major, ld even, columns >= p are zero
   int q, p, ld;
   int max_sweeps;
@@ -138,6 +140,62 @@ __device__ __forceinline__ bool rotate_pair_mem(double* __restrict__ ra, double*
   return true;
 }
 
+// complex rows (planar): gamma = <z_b, z_a> = sum z_a conj(z_b); z_b is first multiplied by the phase gamma/|gamma|, which
+// makes the inner product real and positive, then the real rotation is applied.
+__device__ __forceinline__ bool rotate_pair_cplx(double* __restrict__ ar, double* __restrict__ ai, double* __restrict__ br,
+                                                 double* __restrict__ bi, int ld, double tol, double thr, int lane) {
+  double alpha = 0.0, beta = 0.0, gr = 0.0, gi = 0.0;
+  for (int col = 2 * lane; col < ld; col += 64) {
+    double2 xr = __ldcg(reinterpret_cast<const double2*>(ar + col)), xi = __ldcg(reinterpret_cast<const double2*>(ai + col));
+    double2 yr = __ldcg(reinterpret_cast<const double2*>(br + col)), yi = __ldcg(reinterpret_cast<const double2*>(bi + col));
+    alpha += xr.x * xr.x + xi.x * xi.x + xr.y * xr.y + xi.y * xi.y;
+    beta += yr.x * yr.x + yi.x * yi.x + yr.y * yr.y + yi.y * yi.y;
+    gr += xr.x * yr.x + xi.x * yi.x + xr.y * yr.y + xi.y * yi.y;  // Re(x conj(y))
+    gi += xi.x * yr.x - xr.x * yi.x + xi.y * yr.y - xr.y * yi.y;  // Im(x conj(y))
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gr = warp_sum(gr);
+  gi = warp_sum(gi);
+  if (!(alpha > thr) || !(beta > thr)) return false;
+  double gabs = hypot(gr, gi);
+  double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(gabs > tol * lim)) return false;
+  double c, s;
+  rotation(alpha, beta, gabs, c, s);
+  const double wr = gr / gabs, wi = gi / gabs;  // phase omega
+  for (int col = 2 * lane; col < ld; col += 64) {
+    double2 xr = __ldcg(reinterpret_cast<const double2*>(ar + col)), xi = __ldcg(reinterpret_cast<const double2*>(ai + col));
+    double2 yr = __ldcg(reinterpret_cast<const double2*>(br + col)), yi = __ldcg(reinterpret_cast<const double2*>(bi + col));
+    // y~ = omega * y
+    double2 tr = make_double2(wr * yr.x - wi * yi.x, wr * yr.y - wi * yi.y);
+    double2 ti = make_double2(wr * yi.x + wi * yr.x, wr * yi.y + wi * yr.y);
+    __stcg(reinterpret_cast<double2*>(ar + col), make_double2(c * xr.x - s * tr.x, c * xr.y - s * tr.y));
+    __stcg(reinterpret_cast<double2*>(ai + col), make_double2(c * xi.x - s * ti.x, c * xi.y - s * ti.y));
+    __stcg(reinterpret_cast<double2*>(br + col), make_double2(s * xr.x + c * tr.x, s * xr.y + c * tr.y));
+    __stcg(reinterpret_cast<double2*>(bi + col), make_double2(s * xi.x + c * ti.x, s * xi.y + c * ti.y));
+  }
+  return true;
+}
+
+__device__ __forceinline__ double row_norm2(const JacobiArgs& a, int i, int lane) {
+  const double* ri = a.Z + (size_t)i * a.ld;
+  double acc = 0.0;
+  for (int col = 2 * lane; col < a.ld; col += 64) {
+    double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+    acc += v.x * v.x + v.y * v.y;
+  }
+  if (a.Zi) {
+    const double* ii = a.Zi + (size_t)i * a.ld;
+    for (int col = 2 * lane; col < a.ld; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ii + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+  }
+  return warp_sum(acc);
+}
+
+// NCH > 0: real rows held in registers; NCH == 0: real rows, two passes; NCH == -1: complex rows (planar), two passes
 template <int NCH>
 __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
   const int lane = threadIdx.x & 31;
@@ -153,13 +211,7 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
   // rank-deficient Z (more rows than the row space has dimensions) never converges: the surplus rows are rounding
   // noise that keeps being re-orthogonalised at ever smaller scales.
   for (int i = gw; i < a.q; i += GW) {
-    const double* ri = a.Z + (size_t)i * a.ld;
-    double acc = 0.0;
-    for (int col = 2 * lane; col < a.ld; col += 64) {
-      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
-      acc += v.x * v.x + v.y * v.y;
-    }
-    acc = warp_sum(acc);
+    double acc = row_norm2(a, i, lane);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
@@ -190,7 +242,8 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
         double* rb = a.Z + (size_t)ib * a.ld;
         bool rot;
         if constexpr (NCH > 0) rot = rotate_pair_reg<NCH>(ra, rb, a.ld, a.tol, thr, lane);
-        else rot = rotate_pair_mem(ra, rb, a.ld, a.tol, thr, lane);
+        else if constexpr (NCH == 0) rot = rotate_pair_mem(ra, rb, a.ld, a.tol, thr, lane);
+        else rot = rotate_pair_cplx(ra, a.Zi + (size_t)ia * a.ld, rb, a.Zi + (size_t)ib * a.ld, a.ld, a.tol, thr, lane);
         rotated |= rot;
       }
       grid_sync(a.sync, target);
@@ -202,14 +255,10 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
   }
   // squared norms of the (now mutually orthogonal) rows
   for (int i = gw; i < a.q; i += GW) {
-    const double* ri = a.Z + (size_t)i * a.ld;
-    double acc = 0.0;
-    for (int col = 2 * lane; col < a.ld; col += 64) {
-      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
-      acc += v.x * v.x + v.y * v.y;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) __stcg(a.norms + i, acc > thr ? acc : 0.0);
+    double acc = row_norm2(a, i, lane);
+    if (!(acc > thr)) acc = 0.0;
+    if (a.eigen_mode) acc = sqrt(acc);
+    if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
   // rank sort, descending, ties by index (stable)
@@ -254,14 +303,18 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
 }
 
 // Wn[i][:] = Z[perm[i]][:] / sqrt(sig2[i])  for i < k   (zero rows stay zero)
-__global__ void gather_normalize_kernel(const double* __restrict__ Z, int ld, int p, const int* __restrict__ perm,
-                                        const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
+__global__ void gather_normalize_kernel(const double* __restrict__ Z, const double* __restrict__ Zi, int ld, int p,
+                                        const int* __restrict__ perm, const double* __restrict__ sig2, int eigen_mode, int k,
+                                        double* __restrict__ Wn, double* __restrict__ Wni, double* __restrict__ sigma_out) {
   int i = blockIdx.y;
   if (i >= k) return;
-  double s = sqrt(sig2[i]);
+  double s = eigen_mode ? sig2[i] : sqrt(sig2[i]);  // row norm
   double inv = s > 0.0 ? 1.0 / s : 0.0;
-  const double* src = Z + (size_t)perm[i] * ld;
-  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x) Wn[(size_t)i * p + col] = src[col] * inv;
+  const size_t off = (size_t)perm[i] * ld;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x) {
+    Wn[(size_t)i * p + col] = Z[off + col] * inv;
+    if (Zi) Wni[(size_t)i * p + col] = Zi[off + col] * inv;
+  }
   if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = s;
 }
 
@@ -283,29 +336,40 @@ void launch_jacobi(Ctx* ctx, JacobiArgs& a, int grid) {
 
 }  // namespace
 
-RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, double cutoff, int maxdim, int mindim,
+                   double* sigma_out, int max_sweeps, bool eigen_mode) {
   const int ld = (p + 1) & ~1;
   const int kmax = q < p ? q : p;
+  const bool cplx = Mi != nullptr;
   if (max_sweeps <= 0) max_sweeps = 40;
   QTT_REQUIRE(max_sweeps <= 200, "svd_max_sweeps too large");
   double* Z = ctx->arena.alloc((size_t)q * ld);
+  double* Zi = cplx ? ctx->arena.alloc((size_t)q * ld) : nullptr;
   double* sig2 = ctx->arena.alloc(q);
   double* norms = ctx->arena.alloc(q);
   int* perm = reinterpret_cast<int*>(ctx->arena.alloc((q + 1) / 2 + 1));
   int* info = reinterpret_cast<int*>(ctx->arena.alloc(4));
   double* derr = ctx->arena.alloc(2);
-  if (ld == p) {
-    QTT_CUDA(cudaMemcpyAsync(Z, M, sizeof(double) * (size_t)q * p, cudaMemcpyDeviceToDevice, ctx->stream));
-  } else {
-    pad_rows_kernel<<<ctx->sms * 2, 256, 0, ctx->stream>>>(M, q, p, ld, Z);
-    check_launch(ctx, "pad_rows");
-  }
+  auto stage = [&](const double* src, double* dst) {
+    if (ld == p) {
+      QTT_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)q * p, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      pad_rows_kernel<<<ctx->sms * 2, 256, 0, ctx->stream>>>(src, q, p, ld, dst);
+      check_launch(ctx, "pad_rows");
+    }
+  };
+  stage(M, Z);
+  if (cplx) stage(Mi, Zi);
   QTT_CUDA(cudaMemsetAsync(ctx->d_sync + 8, 0, sizeof(unsigned) * (2 + 200), ctx->stream));
   JacobiArgs a;
-  a.Z = Z; a.q = q; a.p = p; a.ld = ld;
+  a.Z = Z; a.Zi = Zi; a.eigen_mode = eigen_mode ? 1 : 0;
+  a.q = q; a.p = p; a.ld = ld;
   a.max_sweeps = max_sweeps;
   a.tol = sqrt((double)p) * 1.1102230246251565e-16;
-  a.zero_tol2 = (8.0 * a.tol) * (8.0 * a.tol);
+  // rows below zero_tol * |Z|_F are rounding noise of the rotations.  In eigen mode the truncated spectrum is |row| itself
+  // and the reference's cutoffs go down to 1e-15, so the floor is kept as low as the rotation noise allows.
+  const double zt = (eigen_mode ? 2.0 : 8.0) * a.tol;
+  a.zero_tol2 = zt * zt;
   a.sync = ctx->d_sync + 8;
   a.sig2 = sig2; a.perm = perm; a.norms = norms; a.info = info; a.derr = derr;
   a.cutoff = cutoff;
@@ -316,7 +380,8 @@ RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxd
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
   if (grid < 1) grid = 1;
-  if (ld <= 128) launch_jacobi<2>(ctx, a, grid);
+  if (cplx) launch_jacobi<-1>(ctx, a, grid);
+  else if (ld <= 128) launch_jacobi<2>(ctx, a, grid);
   else if (ld <= 256) launch_jacobi<4>(ctx, a, grid);
   else if (ld <= 512) launch_jacobi<8>(ctx, a, grid);
   else if (ld <= 1024) launch_jacobi<16>(ctx, a, grid);
@@ -337,10 +402,15 @@ RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxd
   res.truncerr = *h_err;
   if (!h_info[2]) fail(QTT_ERR_NOCONV, "Jacobi SVD did not converge in %d sweeps (q=%d, p=%d)", max_sweeps, q, p);
   res.Wn = ctx->arena.alloc((size_t)res.k * p);
+  res.Wni = cplx ? ctx->arena.alloc((size_t)res.k * p) : nullptr;
   dim3 grid2((p + 255) / 256, res.k);
-  gather_normalize_kernel<<<grid2, 256, 0, ctx->stream>>>(Z, ld, p, perm, sig2, res.k, res.Wn, sigma_out);
+  gather_normalize_kernel<<<grid2, 256, 0, ctx->stream>>>(Z, Zi, ld, p, perm, sig2, a.eigen_mode, res.k, res.Wn, res.Wni, sigma_out);
   check_launch(ctx, "gather_normalize");
   return res;
+}
+
+RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+  return svd_rows_ex(ctx, M, nullptr, q, p, cutoff, maxdim, mindim, sigma_out, max_sweeps, false);
 }
 
 SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, double cutoff, int maxdim, int mindim, double* A_out,

@@ -1,0 +1,110 @@
+"""GPU parity of MPO.MPS `apply` (density-matrix algorithm), `inner` and the residual metric through the C ABI vs the
+oracle, on the reference's own known-answer cases (test/runtests.jl:184-215 prolongation, :249-274 QFT/DFT/FFT).
+
+Tolerances: sampled function values within 1e-9 of the oracle's relative to max|f| (north-star); DFT vs numpy FFT at
+the input-truncation floor (~3.5e-9 norm-relative at cutoff 1e-15)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dense(psi):
+    return O.mps_to_discrete_function(psi)
+
+
+def sines(n, freqs=(1, 2, 4, 8)):
+    """psi = sum_f sin(2 pi f x) built like runtests.jl:255-257: qtt(sin, ...) + directsum."""
+    return O.mps_add_directsum(*[O.qtt_sin(2 * np.pi * f, n) for f in freqs])
+
+
+@pytest.mark.parametrize("n", [4, 7])
+def test_inner_real_and_complex(lib, n):
+    x = O.random_mps(n, 5, 1)
+    y = O.random_mps(n, 3, 2)
+    assert abs(lib.inner(x, y) - O.mps_inner(x, y)) < 1e-13
+    rng = np.random.default_rng(0)
+    xc = [c + 1j * rng.standard_normal(c.shape) for c in x]
+    yc = [c * (0.3 - 0.8j) for c in y]
+    got, want = lib.inner(xc, yc), O.mps_inner(xc, yc)
+    assert abs(got - want) < 1e-13 * max(1.0, abs(want))
+    got, want = lib.inner(xc, y), O.mps_inner(xc, y)
+    assert abs(got - want) < 1e-13 * max(1.0, abs(want))
+
+
+def test_residual_metric(lib):
+    n = 8
+    A = O.airy_mpo(n, 1.0, 4.0)
+    b = O.boundary_value_mps(n, 0.3, -0.2)
+    x = O.random_mps(n, 6, 3)
+    sq = lib.sqeuclidean((A, x), b)
+    sqn = lib.sqeuclidean_normalized((A, x), b)
+    assert abs(sq - O.sqeuclidean_mps(A, x, b)) < 1e-11 * abs(sq)
+    assert abs(sqn - O.sqeuclidean_normalized_mps(A, x, b)) < 1e-11 * abs(sqn)
+    v = dense(x)
+    r = O.mpo_to_mat(A) @ v - dense(b)
+    assert abs(sq - r @ r) < 1e-10 * (r @ r)
+
+
+@pytest.mark.parametrize("n", [3, 6, 10])
+def test_prolongation_apply_matches_oracle_and_interpolation(lib, n):
+    """apply(P, [psi; dummy]; cutoff=1e-8) (reference src/prolongation.jl:29-45)."""
+    psi = O.vec_to_mps(np.sin(np.pi * O.qtt_xrange(n, 0.0, 1.0)) + 0.25, cutoff=1e-15)
+    P = O.prolongation_mpo(n + 1)
+    dummy = np.zeros((1, 2, 1)); dummy[0, 0, 0] = 1.0
+    ext = list(psi) + [dummy]
+    got = lib.apply(P, ext, cutoff=1e-8)
+    want = O.apply_mpo_mps(P, ext, cutoff=1e-8)
+    assert O.linkdims(got) == O.linkdims(want)
+    fg, fw = dense(got), dense(want)
+    assert np.abs(fg - fw).max() <= 1e-9 * np.abs(fw).max()
+    c = dense(psi)
+    fine = np.empty(2 * c.size)
+    fine[0::2] = c
+    fine[1::2] = 0.5 * (c + np.append(c[1:], 0.0))
+    assert np.abs(fg - fine).max() < 1e-6 * np.abs(fine).max()   # truncation at cutoff 1e-8 (runtests.jl rtol 1e-6)
+
+
+def test_apply_untruncated_is_exact(lib):
+    """cutoff = 0: the result equals the dense operator applied to the dense vector to rounding."""
+    n = 6
+    A = O.airy_mpo(n, 1.0, 3.0)
+    psi = O.random_mps(n, 4, 5)
+    got = lib.apply(A, psi, cutoff=0.0)
+    want = O.mpo_to_mat(A) @ dense(psi)
+    assert np.abs(dense(got) - want).max() < 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n", [5, 8])
+def test_dft_apply_matches_fft_and_oracle(lib, n):
+    """runtests.jl:249-274: reverse(apply(F, psi; cutoff=1e-15)) ~ fft(f)/2^(n/2), and apply_idft_mpo inverts it."""
+    F = O.dft_mpo(n)
+    psi = sines(n)
+    raw = lib.apply(F, psi, cutoff=1e-15)
+    got = O.mps_reverse(raw)
+    f = dense(psi)
+    want_fft = np.fft.fft(f) / 2 ** (n / 2)
+    fg = dense(got)
+    assert np.linalg.norm(fg - want_fft) < 5e-8 * np.linalg.norm(want_fft)
+    fo = dense(O.apply_dft_mpo(psi, cutoff=1e-15, F=F))
+    assert np.abs(fg - fo).max() <= 1e-9 * np.abs(fo).max()
+    # inverse: apply(idft_mpo, reverse(F psi)) ~ psi   (reference src/dft.jl:128-133)
+    Finv = O.idft_mpo(n)
+    back = lib.apply(Finv, O.mps_reverse(got), cutoff=1e-15)
+    assert np.linalg.norm(dense(back) - f) < 5e-8 * np.linalg.norm(f)
+
+
+def test_dft_apply_real_input_complex_operator_bond_dims(lib):
+    """Mixed dtypes (Float64 psi, ComplexF64 MPO) and the kept ranks of the density-matrix truncation."""
+    n = 8
+    F = O.dft_mpo(n)
+    xg = O.qtt_xrange(n, 0.0, 1.0)
+    psi = O.vec_to_mps(np.exp(-40.0 * (xg - 0.4) ** 2) + 0.1 * np.cos(6 * np.pi * xg), cutoff=1e-14)
+    assert all(c.dtype == np.float64 for c in psi)
+    got = lib.apply(F, psi, cutoff=1e-13)
+    want = O.apply_mpo_mps(F, [c.astype(complex) for c in psi], cutoff=1e-13)
+    assert max(O.linkdims(got)) <= max(O.linkdims(want)) + 1
+    fw = dense(want)
+    assert np.abs(dense(got) - fw).max() <= 1e-9 * np.abs(fw).max()
