@@ -144,6 +144,7 @@ def inner(x, y, ctx=None):
     dx, fx = _as_dev_mps(x, ctx)
     dy, fy = _as_dev_mps(y, ctx)
     out = (C.c_double * 2)()
+    cplx = dx.is_complex or dy.is_complex
     try:
         check(ctx.handle, lib.qtt_inner(ctx.handle, dx.handle, dy.handle, out))
     finally:
@@ -151,7 +152,7 @@ def inner(x, y, ctx=None):
             dx.free()
         if fy:
             dy.free()
-    return complex(out[0], out[1]) if (dx.is_complex or dy.is_complex) else out[0]
+    return complex(out[0], out[1]) if cplx else out[0]
 
 
 def _residual(A, x, b, ctx):
