@@ -2,6 +2,8 @@
 // caught here and turned into a status code + message.
 #include "common.cuh"
 #include <mutex>
+#include <map>
+#include <unordered_map>
 
 namespace qtt {
 void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_sweep_params& P, qtt_sweep_info* infos);
@@ -12,18 +14,110 @@ void mps_residual(Ctx* ctx, const Mpo& A, const Mps& x, const Mps& b, double* sq
 static std::string g_error;
 static std::mutex g_mutex;
 
+// ---- caching device allocator ---------------------------------------------------------------------------------
+// cudaMalloc / cudaFree inside a sweep cost 20-100 ms spikes (measured: environment updates of the first round-1 build)
+// and cudaFree synchronises the device.  Blocks are therefore recycled through per-device free lists; a block
+// remembers the stream it was last used on, so re-use on the same stream is ordered by the stream itself and re-use
+// on another stream first waits for the old one.  Everything is released by qtt_pool_trim() / at process exit.
+namespace {
+struct PoolBlock { void* p; size_t bytes; cudaStream_t st; };
+struct DevicePool { std::multimap<size_t, PoolBlock> free_blocks; std::unordered_map<void*, size_t> live; size_t cached = 0; };
+std::mutex g_pool_mutex;
+std::map<int, DevicePool> g_pools;
+thread_local Ctx* tl_ctx = nullptr;
+
+size_t pool_round(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes <= (size_t(1) << 20)) {  // next power of two
+    size_t r = 512;
+    while (r < bytes) r <<= 1;
+    return r;
+  }
+  const size_t q = size_t(1) << 20;
+  return (bytes + q - 1) / q * q;
+}
+}  // namespace
+
+void set_current_ctx(Ctx* c) { tl_ctx = c; }
+
+void* pool_alloc(size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t want = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    DevicePool& P = g_pools[dev];
+    auto it = P.free_blocks.find(want);
+    if (it != P.free_blocks.end()) {
+      PoolBlock b = it->second;
+      P.free_blocks.erase(it);
+      P.cached -= b.bytes;
+      P.live[b.p] = b.bytes;
+      if (b.st != st && b.st != nullptr) cudaStreamSynchronize(b.st);
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pool_trim();  // give the cached blocks back and retry once
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) fail(QTT_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  g_pools[dev].live[p] = want;
+  return p;
+}
+
+void pool_free(void* p, cudaStream_t st) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  DevicePool& P = g_pools[dev];
+  auto it = P.live.find(p);
+  if (it == P.live.end()) {  // not ours (or another device is current): fall back to the driver
+    cudaFree(p);
+    return;
+  }
+  const size_t bytes = it->second;
+  P.live.erase(it);
+  P.free_blocks.emplace(bytes, PoolBlock{p, bytes, st});
+  P.cached += bytes;
+}
+
+void pool_trim() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  DevicePool& P = g_pools[dev];
+  cudaDeviceSynchronize();
+  for (auto& kv : P.free_blocks) cudaFree(kv.second.p);
+  P.free_blocks.clear();
+  P.cached = 0;
+}
+
+// a stream is about to be destroyed: its cached blocks become quiescent
+static void pool_forget_stream(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  for (auto& dp : g_pools)
+    for (auto& kv : dp.second.free_blocks)
+      if (kv.second.st == st) kv.second.st = nullptr;
+}
+
 void dbuf_reserve(DBuf& b, size_t n) {
   if (n <= b.cap && b.p) return;
   size_t cap = n < 16 ? 16 : n;
-  double* np = nullptr;
-  cudaError_t e = cudaMalloc(&np, cap * sizeof(double));
-  if (e != cudaSuccess) fail(QTT_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", cap * sizeof(double), cudaGetErrorString(e));
-  if (b.p) cudaFree(b.p);  // implicit device synchronisation: earlier readers of the old buffer have finished
+  cudaStream_t st = tl_ctx ? tl_ctx->stream : nullptr;
+  double* np = static_cast<double*>(pool_alloc(cap * sizeof(double), st));
+  if (b.p) pool_free(b.p, b.st);  // earlier readers of the old block are ahead of any later writer in stream order
   b.p = np;
   b.cap = cap;
+  b.st = st;
 }
 void dbuf_free(DBuf& b) {
-  if (b.p) cudaFree(b.p);
+  if (b.p) pool_free(b.p, b.st);
   b.p = nullptr;
   b.cap = 0;
 }
@@ -34,23 +128,20 @@ Mpo::~Mpo() { for (auto& c : core) dbuf_free(c); }
 void Ctx::ensure_arena(size_t bytes) {
   if (bytes <= arena.cap) return;
   if (arena.top != 0) fail(QTT_ERR_ALLOC, "internal: arena growth requested while in use");
-  QTT_CUDA(cudaStreamSynchronize(stream));
-  if (arena.base) cudaFree(arena.base);
+  if (arena.base) pool_free(arena.base, stream);
   size_t cap = bytes + bytes / 4 + (1 << 20);
   arena.base = nullptr;
   arena.cap = 0;
-  cudaError_t e = cudaMalloc(&arena.base, cap);
-  if (e != cudaSuccess) fail(QTT_ERR_ALLOC, "workspace cudaMalloc of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+  arena.base = static_cast<char*>(pool_alloc(cap, stream));
   arena.cap = cap;
 }
 
 // RAII device scratch for the fine-grained entry points
 struct Scratch {
   std::vector<double*> ptrs;
+  cudaStream_t st = tl_ctx ? tl_ctx->stream : nullptr;
   double* get(size_t n) {
-    double* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (n < 2 ? 2 : n) * sizeof(double));
-    if (e != cudaSuccess) fail(QTT_ERR_ALLOC, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    double* p = static_cast<double*>(pool_alloc((n < 2 ? 2 : n) * sizeof(double), st));
     ptrs.push_back(p);
     return p;
   }
@@ -59,7 +150,7 @@ struct Scratch {
     QTT_CUDA(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     return p;
   }
-  ~Scratch() { for (double* p : ptrs) cudaFree(p); }
+  ~Scratch() { for (double* p : ptrs) pool_free(p, st); }
 };
 
 // host column-major (d0, d1, ...) == row-major [.., d1, d0]; bring to the row-major order `perm` of those reversed dims
@@ -91,7 +182,7 @@ float timed_reps(Ctx* ctx, int reps, F&& body) {
 
 using namespace qtt;
 
-#define QTT_TRY(ctxp) try {
+#define QTT_TRY(ctxp) try { qtt::set_current_ctx(ctxp);
 #define QTT_CATCH(ctxp)                                                     \
   }                                                                         \
   catch (const qtt::Error& e) {                                             \
@@ -153,14 +244,15 @@ void qtt_ctx_destroy(qtt_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->arena.base) cudaFree(c->arena.base);
+  if (c->arena.base) pool_free(c->arena.base, c->stream);
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->d_partial) cudaFree(c->d_partial);
   if (c->d_sync) cudaFree(c->d_sync);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream) { pool_forget_stream(c->stream); cudaStreamDestroy(c->stream); }
+  pool_trim();
   delete c;
 }
 

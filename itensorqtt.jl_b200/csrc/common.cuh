@@ -46,6 +46,7 @@ struct Error : std::runtime_error {
 struct DBuf {
   double* p = nullptr;
   size_t cap = 0;  // elements
+  cudaStream_t st = nullptr;  // stream of the context that allocated it (caching allocator, capi.cu)
 };
 
 struct Ctx;
@@ -114,6 +115,10 @@ struct Mpo {
 };
 
 void dbuf_reserve(DBuf& b, size_t n_elems);
+void* pool_alloc(size_t bytes, cudaStream_t st);
+void pool_free(void* p, cudaStream_t st);
+void pool_trim();
+void set_current_ctx(Ctx* c);
 void dbuf_free(DBuf& b);
 
 // ------------------------------------------------------------------ GEMM core (gemm_dmma.cu)

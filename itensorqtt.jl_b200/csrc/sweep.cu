@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <chrono>
 #include <functional>
+#include <cstdlib>
 
 namespace qtt {
 
@@ -22,6 +23,7 @@ void kry_dots_acc(Ctx*, const double*, int, size_t, const double*, double*);
 namespace {
 
 constexpr int KD_MAX = 62;
+int g_trace_sweeps = 0;  // sweeps completed in this process (QTT_DUMP addresses a sweep by this count)
 // layout of the scalar block in ctx->d_scal (doubles)
 enum {
   S_BETA = 0, S_NRES2 = 1, S_R0N2 = 2, S_DONE = 3, S_K = 4, S_NRES = 5, S_THETA = 6, S_TMP = 7,
@@ -477,6 +479,15 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   QTT_REQUIRE(is_lin || P.solver == QTT_SOLVER_LANCZOS, "solver kind %d not available in this build", P.solver);
   QTT_REQUIRE(!is_lin || b, "linsolve needs a right-hand side");
 
+  // QTT_TRACE=1 (with profiling enabled): per-bond phase timings on stderr; QTT_DUMP="sweep,dir,bond,path" saves that bond's phi
+  const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
+  int dump_sw = -1, dump_dir = -1, dump_bond = -1;
+  static char dump_path_buf[512];
+  const char* dump_path = nullptr;
+  double* dump_buf = nullptr;
+  DBuf dump_store;
+  if (trace && getenv("QTT_DUMP") && sscanf(getenv("QTT_DUMP"), "%d,%d,%d,%500s", &dump_sw, &dump_dir, &dump_bond, dump_path_buf) == 4)
+    dump_path = dump_path_buf;
   if (!P.x0_canonical) right_orthonormalize(ctx, x);
 
   std::vector<DBuf> LA(n + 1), RA(n + 1), LB(n + 1), RB(n + 1);
@@ -562,6 +573,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const double* Rp = RA[j + 2].p;
           MatvecFn mv = [&](const double* in, double* out) { matvec2(ctx, Lp, W12, Rp, in, out, chil, chir, wl, wr, mvscr); };
           LocalStats st;
+          const double tk0 = info.t_krylov, ts0 = info.t_svd, te0 = info.t_env;
           const int kdl = (size_t)kd < len ? kd : (int)len;  // a Krylov space cannot exceed the local dimension
           {
             PhaseTimer pt(ctx, &info.t_krylov);
@@ -591,6 +603,11 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           if (maxdim > 0 && maxdim < kcap) kcap = maxdim;
           dbuf_reserve(x.core[j], (size_t)2 * chil * kcap);
           dbuf_reserve(x.core[j + 1], (size_t)2 * chir * kcap);
+          if (trace && dump_path && g_trace_sweeps == dump_sw && dir == dump_dir && j == dump_bond) {
+            dbuf_reserve(dump_store, len);
+            dump_buf = dump_store.p;
+            QTT_CUDA(cudaMemcpyAsync(dump_buf, phi, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+          }
           SplitResult sr;
           {
             PhaseTimer pt(ctx, &info.t_svd);
@@ -607,10 +624,21 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
             if (dir == 0 && j < n - 2) update_left(j);
             else if (dir == 1 && j > 0) update_right(j + 1);
           }
+          if (trace) {
+            fprintf(stderr, "[qtt trace] sweep %d dir %d bond %d chi (%d,%d,%d)->%d krylov %.3f ms svd %.3f ms (%d jacobi sweeps) env %.3f ms\n", sw, dir,
+                    j, chil, chim, chir, sr.rank, info.t_krylov - tk0, info.t_svd - ts0, sr.sweeps, info.t_env - te0);
+            if (dump_path && g_trace_sweeps == dump_sw && dir == dump_dir && j == dump_bond) {
+              // debugging aid: the solved two-site tensor of one bond, as raw doubles [a][s1][s2][c]
+              std::vector<double> h(len);
+              QTT_CUDA(cudaMemcpy(h.data(), dump_buf, len * sizeof(double), cudaMemcpyDeviceToHost));
+              if (FILE* f = fopen(dump_path, "wb")) { fwrite(h.data(), sizeof(double), len, f); fclose(f); }
+            }
+          }
         }
       }
       QTT_CUDA(cudaEventRecord(evs1, ctx->stream));
       QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+      ++g_trace_sweeps;
       info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       {
         float ms = 0.f;
@@ -631,9 +659,11 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
     cudaEventDestroy(evs1);
   } catch (...) {
     cleanup();
+    dbuf_free(dump_store);
     throw;
   }
   cleanup();
+  dbuf_free(dump_store);
 }
 
 }  // namespace qtt
