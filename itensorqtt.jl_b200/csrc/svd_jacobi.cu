@@ -12,6 +12,7 @@
 // the truncation scan) is ONE cooperative persistent kernel with a monotonic-counter grid barrier between rounds, so
 // there is no host round trip until the kept rank is read back.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace qtt {
 
@@ -410,6 +411,9 @@ RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, do
 }
 
 RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+  // fast path: rank-revealing QR + Jacobi on the rows of R (svd_qr.cu); QTT_SVD=jacobi forces the plain kernel (A/B runs)
+  static const bool plain = getenv("QTT_SVD") != nullptr && std::string(getenv("QTT_SVD")) == "jacobi";
+  if (!plain && svd_rows_qr_supported(q, p)) return svd_rows_qr(ctx, M, q, p, cutoff, maxdim, mindim, sigma_out, max_sweeps);
   return svd_rows_ex(ctx, M, nullptr, q, p, cutoff, maxdim, mindim, sigma_out, max_sweeps, false);
 }
 

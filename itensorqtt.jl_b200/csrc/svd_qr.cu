@@ -1,0 +1,727 @@
+// Site splitting, fast path (real FP64): rank-revealing Householder QR followed by one-sided Jacobi on the rows of R.
+// Replaces `replacebond!` -> `svd` (LAPACK gesdd) -> `truncate!`; this is the "QR followed by
+// a one-sided Jacobi SVD kernel with cutoff/maxdim truncation" of the north star (Drmac-Veselic preconditioning).
+//
+// Problem: Z (q x p, rows z_i) -> the k dominant right singular vectors as orthonormal rows Wn (k x p) + sigma^2.
+// Plain one-sided Jacobi on the rows of Z needs 14 sweeps on a flat 512 x 512 spectrum and 24-34 sweeps on the graded /
+// numerically rank-deficient two-site tensors of a converging sweep (measured, profiles/r01_svd_notes.md); each sweep
+// is q-1 latency-bound rounds.  Here instead
+//   1. Z^T = Q R by Householder reflections applied from the RIGHT to the rows of the stacked matrix SE = [Z; I_p]
+//      (so the identity block accumulates Q).  Panels of up to 32 rows are chosen by residual norm (largest first,
+//      exact norms recomputed after every panel) and pivoted inside the panel; the factorisation STOPS as soon as
+//      every remaining residual norm is below the zero threshold, so its cost is proportional to the numerical rank r.
+//   2. Y = (SE[:, :r])^T = [R | Q^T] (r rows): one-sided Jacobi orthogonalises the rows of R (rotation angles from the
+//      R part only) and carries the Q^T part along.  R R^T is far closer to diagonal than Z Z^T (9-11 sweeps instead
+//      of up to 34, and only r-1 rounds per sweep).  On convergence row i is [sigma_i u_i^T | v_i^T]: the carried part
+//      is already the orthonormal right singular vector, no division by sigma_i, so tiny sigma cost no accuracy.
+//   3. descending sort of sigma^2, NDTensors.truncate! rule, gather of the kept rows.
+// Everything is enqueued without a host round trip; only the kept rank is read back at the end.
+#include "common.cuh"
+
+namespace qtt {
+namespace {
+
+constexpr int NB = 32;          // panel width (reflectors per panel)
+constexpr int PANEL_T = 512;    // threads of the panel / apply kernels (16 warps)
+constexpr int PANEL_W = PANEL_T / 32;
+
+// device-resident control block
+struct QrCtl {
+  int r;        // reflectors (= rows of R) so far
+  int done;     // no row above the zero threshold is left, or r reached min(q, p)
+  int nbp;      // reflectors produced by the most recent panel (0 = the panel kernel did nothing)
+  int serial;   // panel serial number
+  double F2;    // |Z|_F^2
+  double thr;   // zero threshold on squared norms
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// SE rows [0,q) = Z (zero padded to ldp), rows [q, q+p) = identity; norms[i] = |z_i|^2
+__global__ void qr_init_kernel(const double* __restrict__ M, int q, int p, int ldp, double* __restrict__ SE, double* __restrict__ norms,
+                               int* __restrict__ rowstate, int* __restrict__ inpanel, QrCtl* ctl) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int GW = (gridDim.x * blockDim.x) >> 5;
+  for (int i = gw; i < q + p; i += GW) {
+    double* dst = SE + (size_t)i * ldp;
+    if (i < q) {
+      const double* src = M + (size_t)i * p;
+      double acc = 0.0;
+      for (int c = lane; c < ldp; c += 32) {
+        double v = c < p ? src[c] : 0.0;
+        dst[c] = v;
+        acc += v * v;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        norms[i] = acc;
+        rowstate[i] = 0;
+        inpanel[i] = -1;
+      }
+    } else {
+      const int d = i - q;
+      for (int c = lane; c < ldp; c += 32) dst[c] = (c == d) ? 1.0 : 0.0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->r = 0; ctl->done = 0; ctl->nbp = 0; ctl->serial = 0; ctl->F2 = -1.0; ctl->thr = 0.0;
+  }
+}
+
+// One panel: select up to NB unprocessed rows by residual norm, Householder-factor them with in-panel pivoting.
+// Vp (NB x ldp) receives the reflectors (v_j = 1, zeros left of j), taus their scalars.
+__global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ SE, int q, int p, int ldp, int rmax, int nb, double zero_tol2,
+                                                           const double* __restrict__ norms, int* __restrict__ rowstate,
+                                                           int* __restrict__ inpanel, double* __restrict__ Vp,
+                                                           double* __restrict__ taus, QrCtl* ctl) {
+  extern __shared__ double sm[];
+  double* P = sm;                                      // [NB][ldp]
+  double* nrm = sm + (size_t)nb * ldp;                 // [q] candidate norms (<0: not a candidate)
+  __shared__ int sel[NB];
+  __shared__ int proc[NB];      // in-panel: 1 once the row has become a reflector
+  __shared__ int order[NB];     // order[t] = panel slot that became reflector t
+  __shared__ double res[NB];
+  __shared__ double beta_s[NB];
+  __shared__ double tau_s[NB];
+  __shared__ int s_nsel, s_piv, s_stop;
+  __shared__ double s_tau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) ctl->nbp = 0;
+  if (ctl->done) return;
+  const int r0 = ctl->r;
+  const int serial = ctl->serial;
+  // |Z|_F^2 once (the initial norms are the full row norms)
+  if (ctl->F2 < 0.0) {
+    __shared__ double red[PANEL_W];
+    double acc = 0.0;
+    for (int i = tid; i < q; i += PANEL_T) acc += norms[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int k = 0; k < PANEL_W; ++k) s += red[k];
+      ctl->F2 = s;
+      ctl->thr = zero_tol2 * s;
+    }
+    __syncthreads();
+  }
+  const double thr = ctl->thr;
+  int want = rmax - r0;
+  if (want > nb) want = nb;
+  // ---- selection: the `want` largest residual norms among the unprocessed rows, if above the threshold
+  for (int i = tid; i < q; i += PANEL_T) nrm[i] = (rowstate[i] == 0) ? norms[i] : -1.0;
+  if (tid < NB) { sel[tid] = -1; proc[tid] = 0; }
+  if (tid == 0) { s_nsel = 0; s_stop = 0; }
+  __syncthreads();
+  for (int i = tid; i < q; i += PANEL_T) {
+    const double ni = nrm[i];
+    if (!(ni > thr)) continue;
+    int rank = 0;
+    for (int j = 0; j < q; ++j) {
+      const double nj = nrm[j];
+      rank += (nj > ni) || (nj == ni && j < i);
+    }
+    if (rank < want) {
+      sel[rank] = i;
+      atomicAdd(&s_nsel, 1);
+    }
+  }
+  __syncthreads();
+  const int nsel = s_nsel;  // ranks 0..nsel-1 are all filled (ranks are distinct and dense among rows above thr)
+  if (nsel == 0) {
+    if (tid == 0) ctl->done = 1;
+    return;
+  }
+  // ---- load the panel rows
+  for (int u = warp; u < nsel; u += PANEL_W) {
+    const double* src = SE + (size_t)sel[u] * ldp;
+    for (int c = lane; c < ldp; c += 32) P[(size_t)u * ldp + c] = src[c];
+  }
+  __syncthreads();
+  int nfin = 0;
+  for (int t = 0; t < nsel; ++t) {
+    const int j = r0 + t;
+    // residual norms of the not yet processed panel rows
+    for (int u = warp; u < nsel; u += PANEL_W) {
+      double acc = -1.0;
+      if (!proc[u]) {
+        acc = 0.0;
+        const double* row = P + (size_t)u * ldp;
+        for (int c = j + lane; c < p; c += 32) acc += row[c] * row[c];
+        acc = warp_sum(acc);
+      }
+      if (lane == 0) res[u] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double best = lane < nsel ? res[lane] : -1.0;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        if (!(best > thr)) s_stop = 1;
+        s_piv = bi;
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
+    const int piv = s_piv;
+    double* x = P + (size_t)piv * ldp;
+    if (warp == 0) {
+      // dlarfg: beta = -sign(x_j) |x[j:]|, tau = (beta - x_j) / beta, v = x[j+1:] / (x_j - beta), v_j = 1
+      const double xj = x[j];
+      const double nrmx = sqrt(res[piv]);
+      const double beta = -copysign(nrmx, xj);
+      const double tau = (beta - xj) / beta;
+      const double scale = 1.0 / (xj - beta);
+      for (int c = j + 1 + lane; c < p; c += 32) x[c] *= scale;
+      __syncwarp();
+      if (lane == 0) {
+        x[j] = 1.0;
+        beta_s[t] = beta;
+        tau_s[t] = tau;
+        s_tau = tau;
+        order[t] = piv;
+        proc[piv] = 1;
+      }
+    }
+    __syncthreads();
+    const double tau = s_tau;
+    for (int u = warp; u < nsel; u += PANEL_W) {
+      if (proc[u]) continue;
+      double* row = P + (size_t)u * ldp;
+      double d = 0.0;
+      for (int c = j + lane; c < p; c += 32) d += row[c] * x[c];
+      d = warp_sum(d) * tau;
+      for (int c = j + lane; c < p; c += 32) row[c] -= d * x[c];
+    }
+    nfin = t + 1;
+    __syncthreads();
+  }
+  // ---- write back: reflectors, finished rows of R^T, the partially updated leftovers
+  for (int t = warp; t < nb; t += PANEL_W) {
+    double* vrow = Vp + (size_t)t * ldp;
+    if (t < nfin) {
+      const double* x = P + (size_t)order[t] * ldp;
+      const int j = r0 + t;
+      for (int c = lane; c < ldp; c += 32) vrow[c] = (c >= j && c < p) ? x[c] : 0.0;
+    }
+  }
+  for (int u = warp; u < nsel; u += PANEL_W) {
+    double* dst = SE + (size_t)sel[u] * ldp;
+    const double* row = P + (size_t)u * ldp;
+    if (proc[u]) {
+      int t = 0;
+      for (int k = 0; k < nfin; ++k)
+        if (order[k] == u) t = k;
+      const int j = r0 + t;
+      for (int c = r0 + lane; c < ldp; c += 32) dst[c] = c < j ? row[c] : (c == j ? beta_s[t] : 0.0);
+      if (lane == 0) rowstate[sel[u]] = 1;
+    } else {
+      for (int c = r0 + lane; c < ldp; c += 32) dst[c] = row[c];
+    }
+    if (lane == 0) inpanel[sel[u]] = serial;
+  }
+  if (tid < nfin) taus[tid] = tau_s[tid];
+  if (tid == 0) {
+    ctl->r = r0 + nfin;
+    ctl->nbp = nfin;
+    if (r0 + nfin >= rmax) ctl->done = 1;
+  }
+}
+
+// Applies the panel's reflectors (in order) from the right to every row of SE that was not in the panel, and refreshes
+// the residual norms |z_i[r:]|^2 of all unprocessed rows.  NPL = row elements per lane.
+template <int NPL>
+__global__ void __launch_bounds__(PANEL_T) qr_apply_kernel(double* __restrict__ SE, int q, int p, int ldp, const int* __restrict__ rowstate,
+                                                           const int* __restrict__ inpanel, const double* __restrict__ Vp,
+                                                           const double* __restrict__ taus, double* __restrict__ norms, QrCtl* ctl) {
+  extern __shared__ double sm[];
+  const int nbp = ctl->nbp;
+  if (nbp == 0) return;
+  const int serial = ctl->serial;
+  const int rnew = ctl->r;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* V = sm;  // [nbp][ldp]
+  for (int i = tid; i < nbp * ldp; i += PANEL_T) V[i] = Vp[i];
+  __shared__ double tau_s[NB];
+  if (tid < nbp) tau_s[tid] = taus[tid];
+  __syncthreads();
+  const int gw = blockIdx.x * PANEL_W + warp;
+  const int GW = gridDim.x * PANEL_W;
+  for (int i = gw; i < q + p; i += GW) {
+    if (i < q && rowstate[i] == 1) continue;
+    const bool inpan = i < q && inpanel[i] == serial;
+    double* row = SE + (size_t)i * ldp;
+    double x[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const int c = lane + 32 * k;
+      x[k] = c < p ? row[c] : 0.0;
+    }
+    if (!inpan) {
+      for (int t = 0; t < nbp; ++t) {
+        const double* v = V + (size_t)t * ldp;
+        double d = 0.0;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+          const int c = lane + 32 * k;
+          if (c < p) d += x[k] * v[c];
+        }
+        d = warp_sum(d) * tau_s[t];
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+          const int c = lane + 32 * k;
+          if (c < p) x[k] -= d * v[c];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < p) row[c] = x[k];
+      }
+    }
+    if (i < q) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c >= rnew && c < p) acc += x[k] * x[k];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) norms[i] = acc;
+    }
+  }
+}
+
+// generic row length: rows stay in global / L1
+__global__ void __launch_bounds__(PANEL_T) qr_apply_generic_kernel(double* __restrict__ SE, int q, int p, int ldp,
+                                                                   const int* __restrict__ rowstate, const int* __restrict__ inpanel,
+                                                                   const double* __restrict__ Vp, const double* __restrict__ taus,
+                                                                   double* __restrict__ norms, QrCtl* ctl) {
+  const int nbp = ctl->nbp;
+  if (nbp == 0) return;
+  const int serial = ctl->serial;
+  const int rnew = ctl->r;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * PANEL_W + warp;
+  const int GW = gridDim.x * PANEL_W;
+  for (int i = gw; i < q + p; i += GW) {
+    if (i < q && rowstate[i] == 1) continue;
+    const bool inpan = i < q && inpanel[i] == serial;
+    double* row = SE + (size_t)i * ldp;
+    if (!inpan) {
+      for (int t = 0; t < nbp; ++t) {
+        const double* v = Vp + (size_t)t * ldp;
+        double d = 0.0;
+        for (int c = lane; c < p; c += 32) d += row[c] * v[c];
+        d = warp_sum(d) * taus[t];
+        for (int c = lane; c < p; c += 32) row[c] -= d * v[c];
+        __syncwarp();
+      }
+    }
+    if (i < q) {
+      double acc = 0.0;
+      for (int c = rnew + lane; c < p; c += 32) acc += row[c] * row[c];
+      acc = warp_sum(acc);
+      if (lane == 0) norms[i] = acc;
+    }
+  }
+}
+
+__global__ void qr_next_panel_kernel(QrCtl* ctl) { ctl->serial += 1; }
+
+// Y[j][i] = SE[i][j] for j < r (tiled transpose); columns [q, qd) of Y are zero padding.
+__global__ void build_y_kernel(const double* __restrict__ SE, int q, int p, int ldp, int qd, int ldy, double* __restrict__ Y, const QrCtl* ctl) {
+  __shared__ double tile[32][33];
+  const int r = ctl->r;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.x * 32;  // SE row block
+  const int j0 = blockIdx.y * 32;  // SE column block (= Y row block)
+  if (j0 >= r) return;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int i = i0 + ty + k, j = j0 + tx;
+    tile[ty + k][tx] = (i < q + p && j < r) ? SE[(size_t)i * ldp + j] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int j = j0 + ty + k, i = i0 + tx;
+    if (j < r && i < q + p) {
+      const int col = i < q ? i : (qd + (i - q));
+      Y[(size_t)j * ldy + col] = tile[tx][ty + k];
+    }
+  }
+  if (qd != q && blockIdx.x == 0) {
+    for (int j = j0 + ty * 32 + tx; j < j0 + 32 && j < r; j += 256) Y[(size_t)j * ldy + q] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ Jacobi on the rows of [R | Q^T]
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct JqArgs {
+  double* Y;       // [rcap][ld]
+  int ld, ndot;    // row stride / length; the rotation angles use columns [0, ndot)
+  int kmax;        // min(q, p): length of the spectrum that is truncated (entries beyond r are zero)
+  int max_sweeps;
+  double tol;
+  unsigned* sync;
+  double* sig2;    // [kmax]
+  int* perm;       // [kmax]
+  double* norms;   // [rcap]
+  int* info;       // [0] kept rank, [1] sweeps, [2] converged, [3] r
+  double* derr;
+  double cutoff;
+  int maxdim, mindim;
+  const QrCtl* ctl;
+};
+
+__device__ __forceinline__ void jrotation(double alpha, double beta, double gamma, double& c, double& s) {
+  double zeta = (beta - alpha) / (2.0 * gamma);
+  double t;
+  if (fabs(zeta) > 1e150) t = 0.5 / zeta;
+  else t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  c = rsqrt(1.0 + t * t);
+  s = c * t;
+}
+
+template <int NCH>
+__device__ __forceinline__ bool jq_rotate_reg(double* __restrict__ ra, double* __restrict__ rb, int ld, int ndot, double tol, double thr,
+                                              int lane) {
+  double2 za[NCH], zb[NCH];
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      za[k] = __ldcg(reinterpret_cast<const double2*>(ra + col));
+      zb[k] = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    } else {
+      za[k] = make_double2(0.0, 0.0);
+      zb[k] = make_double2(0.0, 0.0);
+    }
+    if (col < ndot) {
+      alpha += za[k].x * za[k].x + za[k].y * za[k].y;
+      beta += zb[k].x * zb[k].x + zb[k].y * zb[k].y;
+      gamma += za[k].x * zb[k].x + za[k].y * zb[k].y;
+    }
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gamma = warp_sum(gamma);
+  if (!(alpha > thr) || !(beta > thr)) return false;
+  const double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
+  double c, s;
+  jrotation(alpha, beta, gamma, c, s);
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      __stcg(reinterpret_cast<double2*>(ra + col), make_double2(c * za[k].x - s * zb[k].x, c * za[k].y - s * zb[k].y));
+      __stcg(reinterpret_cast<double2*>(rb + col), make_double2(s * za[k].x + c * zb[k].x, s * za[k].y + c * zb[k].y));
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ bool jq_rotate_mem(double* __restrict__ ra, double* __restrict__ rb, int ld, int ndot, double tol, double thr,
+                                              int lane) {
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+  for (int col = 2 * lane; col < ndot; col += 64) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(ra + col));
+    double2 b = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    alpha += a.x * a.x + a.y * a.y;
+    beta += b.x * b.x + b.y * b.y;
+    gamma += a.x * b.x + a.y * b.y;
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gamma = warp_sum(gamma);
+  if (!(alpha > thr) || !(beta > thr)) return false;
+  const double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(fabs(gamma) > tol * lim)) return false;
+  double c, s;
+  jrotation(alpha, beta, gamma, c, s);
+  for (int col = 2 * lane; col < ld; col += 64) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(ra + col));
+    double2 b = __ldcg(reinterpret_cast<const double2*>(rb + col));
+    __stcg(reinterpret_cast<double2*>(ra + col), make_double2(c * a.x - s * b.x, c * a.y - s * b.y));
+    __stcg(reinterpret_cast<double2*>(rb + col), make_double2(s * a.x + c * b.x, s * a.y + c * b.y));
+  }
+  return true;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(64) jacobi_qr_kernel(JqArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int GW = gridDim.x * wpb;
+  const int q = a.ctl->r;  // rows of R
+  const double thr = a.ctl->thr;
+  const int qe = (q + 1) & ~1;
+  const int npairs = qe / 2, rounds = qe - 1;
+  unsigned target = 0;
+  int sweeps = 0;
+  int converged = (q < 2) ? 1 : 0;
+  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
+    bool rotated = false;
+    for (int r = 0; r < rounds; ++r) {
+      for (int i = gw; i < npairs; i += GW) {
+        int ia, ib;
+        if (i == 0) {
+          ia = r;
+          ib = qe - 1;
+        } else {
+          ia = (r + i) % (qe - 1);
+          ib = (r - i + (qe - 1)) % (qe - 1);
+        }
+        if (ia >= q || ib >= q) continue;
+        if (ia > ib) {
+          int tmp = ia;
+          ia = ib;
+          ib = tmp;
+        }
+        double* ra = a.Y + (size_t)ia * a.ld;
+        double* rb = a.Y + (size_t)ib * a.ld;
+        bool rot;
+        if constexpr (NCH > 0) rot = jq_rotate_reg<NCH>(ra, rb, a.ld, a.ndot, a.tol, thr, lane);
+        else rot = jq_rotate_mem(ra, rb, a.ld, a.ndot, a.tol, thr, lane);
+        rotated |= rot;
+      }
+      grid_sync(a.sync, target);
+    }
+    if (rotated && lane == 0) atomicAdd(a.sync + 2 + sw, 1u);
+    grid_sync(a.sync, target);
+    sweeps = sw + 1;
+    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
+  }
+  // sigma_i^2 = |R part of row i|^2
+  for (int i = gw; i < q; i += GW) {
+    const double* ri = a.Y + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ndot; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (!(acc > thr)) acc = 0.0;
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  // rank sort, descending, ties by index; entries [q, kmax) of the spectrum are exact zeros
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
+    if (i < q) {
+      const double ni = __ldcg(a.norms + i);
+      int rank = 0;
+      for (int j = 0; j < q; ++j) {
+        const double nj = __ldcg(a.norms + j);
+        rank += (nj > ni) || (nj == ni && j < i);
+      }
+      a.perm[rank] = i;
+      a.sig2[rank] = ni;
+    } else {
+      a.perm[i] = -1;
+      a.sig2[i] = 0.0;
+    }
+  }
+  grid_sync(a.sync, target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // NDTensors.truncate! on P = sigma^2 descending
+    const int len = a.kmax;
+    int n = len;
+    double err = 0.0;
+    int maxdim = a.maxdim < len ? a.maxdim : len;
+    int mindim = a.mindim > 1 ? a.mindim : 1;
+    if (len > 1) {
+      while (n > maxdim) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      double scale = 0.0;
+      for (int i = 0; i < len; ++i) scale += __ldcg(a.sig2 + i);
+      if (scale == 0.0) scale = 1.0;
+      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      err /= scale;
+    }
+    if (n < 1) n = 1;
+    a.info[0] = n;
+    a.info[1] = sweeps;
+    a.info[2] = converged;
+    a.info[3] = q;
+    a.derr[0] = err;
+  }
+}
+
+// Wn[i][:] = carried (Q^T) part of row perm[i]; rows beyond the numerical rank are zero
+__global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
+                                   const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
+  const int i = blockIdx.y;
+  if (i >= k) return;
+  const int src = perm[i];
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x)
+    Wn[(size_t)i * p + col] = src >= 0 ? Y[(size_t)src * ld + off + col] : 0.0;
+  if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = sqrt(sig2[i]);
+}
+
+template <int NCH>
+void launch_jq(Ctx* ctx, JqArgs& a, int grid) {
+  void* args[] = {&a};
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_kernel<NCH>, dim3(grid), dim3(64), args, 0, ctx->stream));
+  ctx->launches++;
+}
+
+template <typename K>
+void set_smem(K kern, size_t bytes) {
+  QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace
+
+static int panel_width(int p) { return p <= 768 ? NB : NB / 2; }
+
+bool svd_rows_qr_supported(int q, int p) {
+  // the panel kernel keeps nb rows of length p (+ q candidate norms) in shared memory
+  const int ldp = (p + 1) & ~1;
+  const size_t smem = ((size_t)panel_width(p) * ldp + q) * sizeof(double);
+  return (p % 2 == 0) && q >= 1 && smem <= 200 * 1024;
+}
+
+RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+  QTT_REQUIRE(svd_rows_qr_supported(q, p), "svd_rows_qr: unsupported shape %d x %d", q, p);
+  const int ldp = (p + 1) & ~1;
+  const int kmax = q < p ? q : p;
+  const int qd = (q + 1) & ~1;
+  const int ldy = qd + ldp;
+  if (max_sweeps <= 0) max_sweeps = 40;
+  QTT_REQUIRE(max_sweeps <= 200, "svd_max_sweeps too large");
+  double* SE = ctx->arena.alloc((size_t)(q + p) * ldp);
+  double* norms = ctx->arena.alloc(q + kmax);
+  int* rowstate = reinterpret_cast<int*>(ctx->arena.alloc(q / 2 + 1));
+  int* inpanel = reinterpret_cast<int*>(ctx->arena.alloc(q / 2 + 1));
+  double* Vp = ctx->arena.alloc((size_t)NB * ldp);
+  double* taus = ctx->arena.alloc(NB);
+  QrCtl* ctl = reinterpret_cast<QrCtl*>(ctx->arena.alloc(8));
+  double* Y = ctx->arena.alloc((size_t)kmax * ldy);
+  double* sig2 = ctx->arena.alloc(kmax);
+  int* perm = reinterpret_cast<int*>(ctx->arena.alloc(kmax / 2 + 1));
+  int* info = reinterpret_cast<int*>(ctx->arena.alloc(4));
+  double* derr = ctx->arena.alloc(2);
+
+  const double tol = sqrt((double)p) * 1.1102230246251565e-16;
+  const double zt = 8.0 * tol;  // rows below zt * |Z|_F are rounding noise: never rotated, sigma reported as 0
+  {
+    int rows = q + p;
+    int grid = (rows + 7) / 8;
+    if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
+    qr_init_kernel<<<grid, 256, 0, ctx->stream>>>(M, q, p, ldp, SE, norms, rowstate, inpanel, ctl);
+    check_launch(ctx, "qr_init");
+  }
+  const int nb = panel_width(p);
+  const size_t smem_panel = ((size_t)nb * ldp + q) * sizeof(double);
+  const size_t smem_apply = (size_t)nb * ldp * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    set_smem(qr_panel_kernel, 200 * 1024);
+    set_smem(qr_apply_kernel<8>, 200 * 1024);
+    set_smem(qr_apply_kernel<16>, 200 * 1024);
+    set_smem(qr_apply_kernel<32>, 200 * 1024);
+    configured = true;
+  }
+  const int npanels = (kmax + nb - 1) / nb;
+  int agrid = (q + p + PANEL_W - 1) / PANEL_W;
+  if (agrid > ctx->sms) agrid = ctx->sms;
+  for (int pn = 0; pn < npanels; ++pn) {
+    qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    check_launch(ctx, "qr_panel");
+    if (p <= 256) qr_apply_kernel<8><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else if (p <= 512) qr_apply_kernel<16><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else if (p <= 1024) qr_apply_kernel<32><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else qr_apply_generic_kernel<<<agrid, PANEL_T, 0, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    check_launch(ctx, "qr_apply");
+    qr_next_panel_kernel<<<1, 1, 0, ctx->stream>>>(ctl);
+    check_launch(ctx, "qr_next_panel");
+  }
+  {
+    dim3 grid((q + p + 31) / 32, (kmax + 31) / 32);
+    build_y_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(SE, q, p, ldp, qd, ldy, Y, ctl);
+    check_launch(ctx, "build_y");
+  }
+  QTT_CUDA(cudaMemsetAsync(ctx->d_sync + 8, 0, sizeof(unsigned) * (2 + 200), ctx->stream));
+  JqArgs a;
+  a.Y = Y; a.ld = ldy; a.ndot = qd; a.kmax = kmax;
+  a.max_sweeps = max_sweeps;
+  a.tol = tol;
+  a.sync = ctx->d_sync + 8;
+  a.sig2 = sig2; a.perm = perm; a.norms = norms + q; a.info = info; a.derr = derr;
+  a.cutoff = cutoff;
+  a.maxdim = maxdim > 0 ? maxdim : kmax;
+  if (a.maxdim > kmax) a.maxdim = kmax;
+  a.mindim = mindim;
+  a.ctl = ctl;
+  const int npairs = ((kmax + 1) & ~1) / 2;
+  int grid = (npairs + 1) / 2;
+  if (grid > ctx->sms) grid = ctx->sms;
+  if (grid < 1) grid = 1;
+  if (ldy <= 128) launch_jq<2>(ctx, a, grid);
+  else if (ldy <= 256) launch_jq<4>(ctx, a, grid);
+  else if (ldy <= 512) launch_jq<8>(ctx, a, grid);
+  else if (ldy <= 1024) launch_jq<16>(ctx, a, grid);
+  else launch_jq<0>(ctx, a, grid);
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi_qr launch failed: %s", cudaGetErrorString(e));
+  }
+  int* h_info = reinterpret_cast<int*>(ctx->h_scal);
+  double* h_err = ctx->h_scal + 8;
+  QTT_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  QTT_CUDA(cudaMemcpyAsync(h_err, derr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  RowSvd res;
+  res.k = h_info[0];
+  res.sweeps = h_info[1];
+  res.truncerr = *h_err;
+  if (!h_info[2]) fail(QTT_ERR_NOCONV, "Jacobi SVD did not converge in %d sweeps (q=%d, p=%d, rank %d)", max_sweeps, q, p, h_info[3]);
+  res.Wn = ctx->arena.alloc((size_t)res.k * p);
+  res.Wni = nullptr;
+  dim3 grid2((p + 255) / 256, res.k);
+  gather_rows_kernel<<<grid2, 256, 0, ctx->stream>>>(Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out);
+  check_launch(ctx, "gather_rows");
+  return res;
+}
+
+}  // namespace qtt
