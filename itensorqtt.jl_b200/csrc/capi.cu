@@ -621,7 +621,7 @@ int qtt_split2(qtt_ctx* ctx, const double* phi, int64_t chia, int64_t chic, int3
 int qtt_krylov_op(qtt_ctx* ctx, int32_t op, const double* V, int64_t nvec, int64_t len, double* w, double* h, double* out, int32_t reps,
                   float* ms) {
   QTT_TRY(ctx)
-  QTT_REQUIRE(ctx && V && w && nvec >= 1 && len >= 1, "qtt_krylov_op: bad arguments");
+  QTT_REQUIRE(ctx && V && w && nvec >= 1 && len >= 1 && (op != 4 || (nvec <= 62 && kry_cgs2_fused_ok(ctx, (size_t)len))), "qtt_krylov_op: bad arguments");
   QTT_CUDA(cudaSetDevice(ctx->device));
   Scratch sc;
   double* dV = sc.upload(ctx, V, (size_t)nvec * len);
@@ -630,6 +630,8 @@ int qtt_krylov_op(qtt_ctx* ctx, int32_t op, const double* V, int64_t nvec, int64
   double* dh = sc.get(nvec + 2);
   double* dh2 = sc.get(nvec + 2);
   double* dn = sc.get(2);
+  double* dS = sc.get(192);
+  QTT_CUDA(cudaMemsetAsync(dS, 0, 192 * sizeof(double), ctx->stream));
   if (h && (op == 1)) QTT_CUDA(cudaMemcpyAsync(dh, h, sizeof(double) * nvec, cudaMemcpyHostToDevice, ctx->stream));
   float t = timed_reps(ctx, reps, [&] {
     QTT_CUDA(cudaMemcpyAsync(dw, dw0, sizeof(double) * len, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -643,20 +645,28 @@ int qtt_krylov_op(qtt_ctx* ctx, int32_t op, const double* V, int64_t nvec, int64
         kry_dots(ctx, dV, (int)nvec, len, dw, dh2);
         kry_axpys_nrm(ctx, dV, (int)nvec, len, dh2, dw, -1.0, dn);
         break;
+      case 4:  // fused CGS2 step: h1 -> S[0..], h2 -> S[64..], |w|^2 -> S[128]
+        kry_cgs2_fused(ctx, dV, (int)nvec, len, dw, nullptr, dS, 0, 64, 128, 129, 0, 0.0, 0.0, 0.0, nullptr);
+        break;
       default: fail(QTT_ERR_ARG, "unknown krylov op %d", op);
     }
   });
   if (ms) *ms = t;
   QTT_CUDA(cudaMemcpyAsync(w, dw, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<double> hh(2 * nvec + 2, 0.0);
+  double nn[2] = {0, 0};
   if (h && (op == 0 || op == 3)) QTT_CUDA(cudaMemcpyAsync(hh.data(), dh, sizeof(double) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
   if (op == 3) QTT_CUDA(cudaMemcpyAsync(hh.data() + nvec, dh2, sizeof(double) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
-  double nn[2] = {0, 0};
+  if (op == 4) {
+    QTT_CUDA(cudaMemcpyAsync(hh.data(), dS, sizeof(double) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
+    QTT_CUDA(cudaMemcpyAsync(hh.data() + nvec, dS + 64, sizeof(double) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
+    QTT_CUDA(cudaMemcpyAsync(nn, dS + 128, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (op == 2 || op == 3) QTT_CUDA(cudaMemcpyAsync(nn, dn, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h && (op == 0 || op == 3))
-    for (int64_t i = 0; i < nvec; ++i) h[i] = hh[i] + (op == 3 ? hh[nvec + i] : 0.0);
-  if (out && (op == 2 || op == 3)) out[0] = sqrt(nn[0]);
+  if (h && (op == 0 || op == 3 || op == 4))
+    for (int64_t i = 0; i < nvec; ++i) h[i] = hh[i] + (op >= 3 ? hh[nvec + i] : 0.0);
+  if (out && (op == 2 || op == 3 || op == 4)) out[0] = sqrt(nn[0]);
   QTT_CATCH(ctx)
 }
 

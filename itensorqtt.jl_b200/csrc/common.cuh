@@ -75,6 +75,7 @@ struct Ctx {
   Arena arena;
   std::string err;
   int64_t launches = 0;
+  unsigned bar_epoch = 0;  // value of the fused-Krylov barrier counter (d_sync + 4) after the launches so far
   bool profiling = false;
   // small device scratch for scalars / flags / partial reductions
   double* d_scal = nullptr;      // 4096 doubles
@@ -156,6 +157,9 @@ void build_w12(Ctx* ctx, const double* W1, const double* W2, double* W12, int wl
 void matvec2(Ctx* ctx, const double* L, const double* W12, const double* R, const double* v, double* out,
              int chil, int chir, int wl, int wr, double* scratch /* >= (wl + wr) * 4 * chil * chir */);
 size_t matvec2_scratch(int chil, int chir, int wl, int wr);
+bool matvec2_fused_ok(int wl, int wr);
+void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R, const double* v, double* out, int chil, int chir,
+                   int wl, int wr, double* scratch /* >= 4 * chil * chir * wr */);
 void env_left(Ctx* ctx, const double* L, const double* x, const double* W, const double* y, double* Lnew,
               int chia, int chib, int chia_y, int chib_y, int w, int w2, double* scratch);
 void env_right(Ctx* ctx, const double* R, const double* x, const double* W, const double* y, double* Rnew,
@@ -168,6 +172,9 @@ void kry_dots_acc(Ctx* ctx, const double* V, int nvec, size_t len, const double*
 void kry_axpys(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign);
 // w += sign * V h and, if nrm2sq_out != null, *nrm2sq_out = ||w_new||^2 (device scalar)
 void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign, double* nrm2sq_out);
+bool kry_cgs2_fused_ok(const Ctx* ctx, size_t len);
+void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, double* vnext, double* S, int off_h1, int off_h2,
+                    int off_nres2, int off_done, int post, double a0, double a1, double tol, volatile double* hstat);
 void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out /* device scalar */);
 void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out,
                   const double* done_dev = nullptr);

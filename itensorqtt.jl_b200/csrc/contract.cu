@@ -6,6 +6,7 @@
 // and the skinny contractions over the MPO indices (K = 2w..4w, not tensor-core shaped) are fused into
 // one bandwidth-bound kernel each, which also performs the layout change the next GEMM needs.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace qtt {
 namespace {
@@ -141,6 +142,12 @@ size_t matvec2_scratch(int chil, int chir, int wl, int wr) {
 
 void matvec2(Ctx* ctx, const double* L, const double* W12, const double* R, const double* v, double* out, int chil, int chir,
              int wl, int wr, double* scratch) {
+  // fused path (matvec_fused.cu): two kernels, no T1 intermediate; QTT_MATVEC=unfused keeps the 4-launch path (A/B runs)
+  static const bool unfused = getenv("QTT_MATVEC") != nullptr && std::string(getenv("QTT_MATVEC")) == "unfused";
+  if (!unfused && matvec2_fused_ok(wl, wr)) {
+    matvec2_fused(ctx, L, W12, R, v, out, chil, chir, wl, wr, scratch);
+    return;
+  }
   const size_t base = (size_t)4 * chil * chir;
   const size_t wmax = wl > wr ? wl : wr;
   double* T1 = scratch;                // [wl][a'][s1 s2][c]; later reused for the split-K partials

@@ -4,6 +4,8 @@
 // to a buffer, reduced in a fixed order by the last CTA to arrive -- no floating-point atomics, so results
 // are bit-reproducible run to run).
 #include "common.cuh"
+#include "krylov_scalars.cuh"
+#include <cstdlib>
 
 namespace qtt {
 namespace {
@@ -173,6 +175,196 @@ __global__ void __launch_bounds__(KT) axpby_kernel(size_t len, double a, const d
   }
 }
 
+
+// ------------------------------------------------------------------ fused CGS2 Arnoldi step (one cooperative launch)
+// w <- (I - V V^T)^2 w with both coefficient sets kept, ||w||, and v_next = w / ||w||: the six launches of the unfused
+// path (dots, axpys, dots, axpys+nrm, scalar update, scale) become ONE persistent kernel with three grid barriers.
+// Each CTA owns a contiguous slice of the vector, which stays in shared memory for the whole step; V is streamed from
+// L2 (the Krylov basis of a chi=256 bond is 31 x 2 MiB and stays L2-resident).  Reductions are per-CTA partials summed
+// in a fixed order by every CTA redundantly, so the coefficients are bit-reproducible and identical in all CTAs.
+struct Cgs2Args {
+  const double* V;
+  int k;
+  size_t len;
+  double* w;        // in: the vector to orthogonalise; out: the orthogonalised, unnormalised vector
+  double* vnext;    // out (may be null): w / ||w||, or zeros when dead
+  double* S;        // scalar block (sweep.cu layout) or null
+  double* part;     // [3][G][64] partials
+  unsigned* bar;    // monotonic barrier counter
+  unsigned epoch;   // counter value at which this launch starts
+  int per;          // slice length per CTA (even)
+  int post;         // 0: store h1, h2, nrm2 only; 1: GMRES update; 2: Lanczos column
+  double a0, a1, tol;
+  volatile double* hstat;
+  int off_h1, off_h2, off_nres2, off_done;
+};
+
+__device__ __forceinline__ unsigned ld_acq_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while ((int)(ld_acq_u32(counter) - target) < 0) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// partial[b][i] = sum over the CTA's slice of V[i][e] * ws[e], all k vectors, 8 at a time (8 x M loads in flight)
+__device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, size_t s0, int n2, double* red /*[nwarps][64]*/,
+                                           double* part_b) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
+  for (int i0 = 0; i0 < a.k; i0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    for (int t2 = tid; t2 < n2; t2 += nthr) {
+      const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
+      const double* vp = a.V + s0 + 2 * (size_t)t2;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (i0 + u < a.k) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len));
+          acc[u] += v.x * wv.x + v.y * wv.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      double v = warp_sum(acc[u]);
+      if (lane == 0) red[warp * 64 + i0 + u] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < a.k) {
+    double s = 0.0;
+    for (int wdx = 0; wdx < nwarps; ++wdx) s += red[wdx * 64 + tid];
+    __stcg(part_b + tid, s);
+  }
+}
+
+// h[i] = sum_b part[b][i] in a fixed order (4 lanes per coefficient), result in shared memory
+__device__ __forceinline__ void reduce_partials(const double* part, int k, int G, double* h_s) {
+  const int tid = threadIdx.x;
+  const int i = tid >> 2, sub = tid & 3;
+  double s = 0.0;
+  if (i < k)
+    for (int b = sub; b < G; b += 4) s += __ldcg(part + (size_t)b * 64 + i);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (i < k && sub == 0) h_s[i] = s;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, size_t s0, int n2, const double* h_s) {
+  const int nthr = blockDim.x;
+  for (int t2 = threadIdx.x; t2 < n2; t2 += nthr) {
+    double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
+    const double* vp = a.V + s0 + 2 * (size_t)t2;
+    for (int i0 = 0; i0 < a.k; i0 += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < a.k) v[u] = __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len));
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < a.k) {
+          const double c = h_s[i0 + u];
+          x.x -= c * v[u].x;
+          x.y -= c * v[u].y;
+        }
+    }
+    *reinterpret_cast<double2*>(ws + 2 * t2) = x;
+  }
+}
+
+
+constexpr int FT_MAX = 512;
+__global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
+  extern __shared__ double dyn[];
+  double* ws = dyn;                // [per]
+  double* red = dyn + a.per;       // [32][64]
+  double* h1 = red + 32 * 64;      // [64]
+  double* h2 = h1 + 64;            // [64]
+  __shared__ double nred[FT_MAX / 32];
+  __shared__ double s_n2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
+  const size_t s0 = (size_t)b * a.per;
+  size_t s1 = s0 + a.per;
+  if (s1 > a.len) s1 = a.len;
+  const int n2 = s0 < a.len ? (int)((s1 - s0) / 2) : 0;
+  // the done flag of the PREVIOUS step decides whether v_next is written as zeros (the flag of this step is only
+  // committed by CTA 0 after the last barrier; see sweep.cu for why lagging by one step is safe)
+  const bool dead = a.S != nullptr && a.S[a.off_done] != 0.0;
+  for (int t2 = tid; t2 < n2; t2 += nthr)
+    *reinterpret_cast<double2*>(ws + 2 * t2) = __ldcg(reinterpret_cast<const double2*>(a.w + s0 + 2 * (size_t)t2));
+  __syncthreads();
+  double* P1 = a.part;
+  double* P2 = a.part + (size_t)G * 64;
+  double* P3 = a.part + (size_t)2 * G * 64;
+  slice_dots(a, ws, s0, n2, red, P1 + (size_t)b * 64);
+  grid_barrier(a.bar, a.epoch + (unsigned)G);
+  reduce_partials(P1, a.k, G, h1);
+  slice_axpys(a, ws, s0, n2, h1);
+  __syncthreads();
+  slice_dots(a, ws, s0, n2, red, P2 + (size_t)b * 64);
+  grid_barrier(a.bar, a.epoch + 2u * (unsigned)G);
+  reduce_partials(P2, a.k, G, h2);
+  slice_axpys(a, ws, s0, n2, h2);
+  __syncthreads();
+  double nacc = 0.0;
+  for (int t2 = tid; t2 < n2; t2 += nthr) {
+    const double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
+    nacc += x.x * x.x + x.y * x.y;
+  }
+  nacc = warp_sum(nacc);
+  if (lane == 0) nred[warp] = nacc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int wdx = 0; wdx < nwarps; ++wdx) s += nred[wdx];
+    __stcg(P3 + b, s);
+  }
+  grid_barrier(a.bar, a.epoch + 3u * (unsigned)G);
+  if (warp == 0) {
+    double s = 0.0;
+    for (int bb = lane; bb < G; bb += 32) s += __ldcg(P3 + bb);
+    s = warp_sum(s);  // xor-butterfly: same order in every CTA
+    if (lane == 0) s_n2 = s;
+  }
+  __syncthreads();
+  const double n2sq = s_n2;
+  const double nrm = sqrt(n2sq);
+  const double inv = (nrm != 0.0 && !dead) ? 1.0 / nrm : 0.0;
+  for (int t2 = tid; t2 < n2; t2 += nthr) {
+    const double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
+    __stcg(reinterpret_cast<double2*>(a.w + s0 + 2 * (size_t)t2), x);
+    if (a.vnext) __stcg(reinterpret_cast<double2*>(a.vnext + s0 + 2 * (size_t)t2), make_double2(x.x * inv, x.y * inv));
+  }
+  if (b == 0 && a.S != nullptr) {
+    if (tid < a.k) {
+      a.S[a.off_h1 + tid] = h1[tid];
+      a.S[a.off_h2 + tid] = h2[tid];
+    }
+    if (tid == 0) a.S[a.off_nres2] = n2sq;
+    __syncthreads();
+    if (tid == 0) {
+      if (a.post == 1) kscal::gmres_step_scalars(a.S, a.k, a.a0, a.a1, a.tol, 64, a.hstat);
+      else if (a.post == 2) kscal::lanczos_step_scalars(a.S, a.k, 64);
+    }
+  }
+}
+
 inline unsigned grid_for(const Ctx* ctx, size_t len, int per_cta) {
   size_t g = (len + per_cta - 1) / per_cta;
   size_t cap = (size_t)ctx->sms * 4;
@@ -244,6 +436,47 @@ void kry_axpby(Ctx* ctx, size_t len, double a, const double* x, double b, const 
   unsigned g = grid_for(ctx, len, KT);
   axpby_kernel<<<g, KT, 0, ctx->stream>>>(len, a, x, b, y, c, z, out);
   check_launch(ctx, "kry_axpby");
+}
+
+}  // namespace qtt
+
+namespace qtt {
+
+bool kry_cgs2_fused_ok(const Ctx* ctx, size_t len) {
+  if (len % 2 != 0) return false;
+  const int G = ctx->sms;
+  size_t per = (len + G - 1) / G;
+  per = (per + 1) & ~size_t(1);
+  return (per + 32 * 64 + 128) * sizeof(double) <= 200 * 1024;
+}
+
+// One fused CGS2 step.  S/off_*: scalar block receiving h1, h2, ||w||^2 (and the solver-specific update `post`).
+void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, double* vnext, double* S, int off_h1, int off_h2,
+                    int off_nres2, int off_done, int post, double a0, double a1, double tol, volatile double* hstat) {
+  QTT_REQUIRE(k >= 1 && k <= 64, "kry_cgs2_fused: k out of range");
+  const int G = ctx->sms;
+  size_t per = (len + G - 1) / G;
+  per = (per + 1) & ~size_t(1);
+  const size_t smem = (per + 32 * 64 + 128) * sizeof(double);
+  static const int fthreads = getenv("QTT_CGS2_THREADS") ? atoi(getenv("QTT_CGS2_THREADS")) : 512;
+  static size_t configured = 0;
+  if (smem > configured) {
+    QTT_CUDA(cudaFuncSetAttribute(cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    configured = 200 * 1024;
+  }
+  Cgs2Args a;
+  a.V = V; a.k = k; a.len = len; a.w = w; a.vnext = vnext; a.S = S;
+  a.part = ctx->partial((size_t)3 * G * 64);
+  a.bar = ctx->d_sync + 4;
+  a.epoch = ctx->bar_epoch;
+  a.per = (int)per;
+  a.post = post;
+  a.a0 = a0; a.a1 = a1; a.tol = tol; a.hstat = hstat;
+  a.off_h1 = off_h1; a.off_h2 = off_h2; a.off_nres2 = off_nres2; a.off_done = off_done;
+  void* args[] = {&a};
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
+  ctx->launches++;
+  ctx->bar_epoch += 3u * (unsigned)G;
 }
 
 }  // namespace qtt

@@ -1,0 +1,523 @@
+// Two-site effective-operator matvec out = L.W1.W2.R.v as TWO fused FP64 tensor-core kernels
+// (replaces upstream `product(P::ProjMPO, v)` = noprime(v*L*W1*W2*R), pattern at reference src/linsolve.jl:71-75,283-288).
+//
+//   K_A  T2[a'][t1 t2][wr][c] = sum_{wl,s1,s2} W12[(wl s1 s2)][(t1 t2 wr)] * ( sum_a L[wl][a'][a] v[a][s1 s2][c] )
+//        The inner sum is a DMMA GEMM over a (K = chi_l).  A CTA owns a block of (a', c) and computes it for ALL wl and
+//        all four (s1 s2): its tile is (wl*BA) x (4*BC) with gathered rows/columns, and the warp tiling is arranged so
+//        that every lane holds all 4*wl partial sums of "its" (a', c) entries.  The skinny contraction with W12 = W1.W2
+//        (K = 4*wl: not tensor-core shaped) is therefore a per-lane register epilogue, and the intermediate
+//        T1[wl][a'][s12][c] of the unfused path (6 MiB written + read at chi = 256) never exists.
+//   K_B  out[(a' t12)][c'] = sum_{(wr c)} T2[(a' t12)][(wr c)] R[(wr c)][c']: a plain GEMM with a small output
+//        (4 chi_l x chi_r) and a long K (wr*chi_r).  To fill 148 SMs with 2 warps per scheduler it uses 32 x 64 CTA tiles
+//        and splits K two ways INSIDE the CTA (two groups of 4 warps), combining through shared memory in a fixed order:
+//        no partial-sum buffer, no extra launch, bit-reproducible.
+// Both kernels stage operands with a 4-deep cp.async pipeline into padded shared-memory tiles (row stride = 4 mod 16
+// doubles: conflict-free LDS.64 fragment loads) and zero-fill ragged edges, so edge bonds take the same path.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace qtt {
+namespace {
+
+constexpr int BK = 16;
+constexpr int STAGES = 4;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+struct MvAArgs {
+  const double* L;    // [wl][chil][chil]  (w, a', a)
+  const double* v;    // [chil][4][chir]   (a, s12, c)
+  const double* W12;  // [4 wl][4 wr]
+  double* T2;         // [chil][4][wr][chir]
+  int chil, chir, wl, wr;
+};
+
+// WL: the left MPO bond dimension (exact); CTA footprint (8*MI*WM) x (8*WN) in (a', c), a warp owns MI a'-subtiles of
+// 8 x 8; VEC = 2 when 16-byte copies are legal.  The per-thread copy descriptors (source pointer, smem offset, edge
+// predicate) are computed once; per k-tile a copy costs one LDGSTS and two integer instructions.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp16(unsigned dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc));
+}
+__device__ __forceinline__ void cp16z(unsigned dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp8z(unsigned dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes));
+}
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
+
+template <int WL, int MI, int WM, int WN, int VEC>
+__global__ void __launch_bounds__(WM* WN * 32) matvec_a_kernel(MvAArgs p) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int BA = 8 * MI * WM, BC = 8 * WN;
+  constexpr int A_LD = BK + 4;            // As[(w, a')][k]
+  constexpr int B_LD = 4 * BC + 4;        // Bs[k][(s, c)]
+  constexpr int A_STAGE = WL * BA * A_LD;
+  constexpr int B_STAGE = BK * B_LD;
+  constexpr int A_CPR = BK / VEC, A_TOTAL = WL * BA * A_CPR, NA = (A_TOTAL + NT - 1) / NT;
+  constexpr int B_CPS = BC / VEC, B_TOTAL = BK * 4 * B_CPS, NB_ = (B_TOTAL + NT - 1) / NT;
+  constexpr bool A_EXACT = (A_TOTAL % NT == 0), B_EXACT = (B_TOTAL % NT == 0);
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+  double* Ws = Bs + STAGES * B_STAGE;     // W12 [4 wl][4 wr]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wa0 = (warp / WN) * 8 * MI, wc0 = (warp % WN) * 8;
+  const int a0 = blockIdx.x * BA, c0 = blockIdx.y * BC;
+  const int wr = p.wr, chil = p.chil, chir = p.chir;
+
+  // programmatic dependent launch: K_B's CTAs may become resident (and run their prologue) while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;\n" ::);
+  for (int i = tid; i < 16 * WL * wr; i += NT) Ws[i] = p.W12[i];
+
+  // ---- copy descriptors, computed once: global source (advanced per k-tile), shared destination of stage 0
+  const double* a_g[NA];
+  unsigned a_s[NA];
+  int a_kleft[NA];   // valid doubles from this chunk's k to the end of the row (0: row out of range / unused slot)
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int id = tid + i * NT;
+    const int r = id / A_CPR, ck = (id % A_CPR) * VEC;
+    const int w = r / BA, ar = r % BA;
+    const int ga = a0 + ar;
+    const bool used = A_EXACT || (id < A_TOTAL);
+    const bool ok = used && (ga < chil);
+    a_g[i] = ok ? (p.L + ((size_t)w * chil + ga) * chil + ck) : p.L;
+    a_s[i] = used ? smem_u32(As + r * A_LD + ck) : 0xffffffffu;
+    a_kleft[i] = ok ? (chil - ck) : 0;
+  }
+  const double* b_g[NB_];
+  unsigned b_s[NB_];
+  int b_kr[NB_], b_cv[NB_];
+#pragma unroll
+  for (int i = 0; i < NB_; ++i) {
+    const int id = tid + i * NT;
+    const int kr = id / (4 * B_CPS), rem = id % (4 * B_CPS);
+    const int sgm = rem / B_CPS, cc = (rem % B_CPS) * VEC;
+    const int gc = c0 + cc;
+    const bool used = B_EXACT || (id < B_TOTAL);
+    int cv = chir - gc;
+    cv = cv < 0 ? 0 : (cv > VEC ? VEC : cv);
+    if (!used) cv = 0;
+    b_g[i] = cv > 0 ? (p.v + ((size_t)kr * 4 + sgm) * chir + gc) : p.v;
+    b_s[i] = used ? smem_u32(Bs + kr * B_LD + sgm * BC + cc) : 0xffffffffu;
+    b_kr[i] = kr;
+    b_cv[i] = cv;
+  }
+  const size_t b_step = (size_t)BK * 4 * chir;
+
+  double acc[WL][MI][4][2];
+#pragma unroll
+  for (int w = 0; w < WL; ++w)
+#pragma unroll
+    for (int m = 0; m < MI; ++m)
+#pragma unroll
+      for (int sg = 0; sg < 4; ++sg) acc[w][m][sg][0] = acc[w][m][sg][1] = 0.0;
+
+  const int KT = (chil + BK - 1) / BK;
+  const int a_frag = (wa0 + g) * A_LD + t;
+  const int b_frag = t * B_LD + wc0 + g;
+  // interior CTA with whole k-tiles: unpredicated 16-byte copies
+  const bool full = (VEC == 2) && (a0 + BA <= chil) && (c0 + BC <= chir) && (chil % BK == 0);
+
+  auto run = [&](auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    int kt_load = 0, st_load = 0;
+    auto issue = [&]() {
+      if (kt_load < KT) {
+        const unsigned aoff = st_load * (A_STAGE * 8), boff = st_load * (B_STAGE * 8);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          if (A_EXACT || a_s[i] != 0xffffffffu) {
+            if constexpr (FULL) {
+              cp16(a_s[i] + aoff, a_g[i]);
+            } else {
+              int valid = a_kleft[i];
+              valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+              const double* src = valid > 0 ? a_g[i] : p.L;
+              if constexpr (VEC == 2) cp16z(a_s[i] + aoff, src, valid * 8);
+              else cp8z(a_s[i] + aoff, src, valid * 8);
+              a_kleft[i] -= BK;
+            }
+            a_g[i] += BK;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NB_; ++i) {
+          if (B_EXACT || b_s[i] != 0xffffffffu) {
+            if constexpr (FULL) {
+              cp16(b_s[i] + boff, b_g[i]);
+            } else {
+              const int valid = (kt_load * BK + b_kr[i] < chil) ? b_cv[i] : 0;
+              const double* src = valid > 0 ? b_g[i] : p.v;
+              if constexpr (VEC == 2) cp16z(b_s[i] + boff, src, valid * 8);
+              else cp8z(b_s[i] + boff, src, valid * 8);
+            }
+            b_g[i] += b_step;
+          }
+        }
+      }
+      cp_async_commit();
+      ++kt_load;
+      st_load = (st_load + 1 == STAGES) ? 0 : st_load + 1;
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue();
+    int st_use = 0;
+    for (int kt = 0; kt < KT; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue();
+      const double* as = As + st_use * A_STAGE + a_frag;
+      const double* bs = Bs + st_use * B_STAGE + b_frag;
+      st_use = (st_use + 1 == STAGES) ? 0 : st_use + 1;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[WL][MI], b[4];
+#pragma unroll
+        for (int w = 0; w < WL; ++w)
+#pragma unroll
+          for (int m = 0; m < MI; ++m) a[w][m] = as[(w * BA + m * 8) * A_LD + kk * 4];
+#pragma unroll
+        for (int sg = 0; sg < 4; ++sg) b[sg] = bs[(kk * 4) * B_LD + sg * BC];
+#pragma unroll
+        for (int w = 0; w < WL; ++w)
+#pragma unroll
+          for (int m = 0; m < MI; ++m)
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) dmma884(acc[w][m][sg][0], acc[w][m][sg][1], a[w][m], b[sg]);
+      }
+    }
+    cp_async_wait<0>();
+  };
+  if (full) run(TrueT{});
+  else run(FalseT{});
+
+  // epilogue: this lane owns (a' = a0 + wa0 + 8m + g, c = c0 + wc0 + 2t, 2t+1) for every (w, s12)
+  const int gc = c0 + wc0 + 2 * t;
+  if (gc >= chir) return;
+  const int nout = 4 * wr;
+  const bool pair = (gc + 1 < chir);
+#pragma unroll
+  for (int m = 0; m < MI; ++m) {
+    const int ga = a0 + wa0 + m * 8 + g;
+    if (ga >= chil) continue;
+    for (int o = 0; o < nout; ++o) {  // o = (t12, wr)
+      double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+      for (int w = 0; w < WL; ++w)
+#pragma unroll
+        for (int sg = 0; sg < 4; ++sg) {
+          const double c = Ws[(w * 4 + sg) * nout + o];
+          o0 += c * acc[w][m][sg][0];
+          o1 += c * acc[w][m][sg][1];
+        }
+      double* dst = p.T2 + ((size_t)ga * nout + o) * chir + gc;
+      if (VEC == 2 && pair) *reinterpret_cast<double2*>(dst) = make_double2(o0, o1);
+      else {
+        dst[0] = o0;
+        if (pair) dst[1] = o1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_B: C (M x N) = A (M x K, lda) . B (K x N, ldb), row-major, CTA tile 32 x 64, 8 warps = 2 K-groups x (2 x 2) warps of
+// 16 x 32; K-group kg handles the k-tiles kt with kt % 2 == kg; the two partial tiles are combined through shared memory.
+struct MvBArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  int M, N, K;
+  long lda, ldb, ldc;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
+  constexpr int BM = 32, BN = 64, NT = 256;
+  constexpr int A_LD = BK + 4, B_LD = BN + 4;
+  constexpr int A_STAGE = BM * A_LD, B_STAGE = BK * B_LD;
+  constexpr int ST = 6;  // stages; two k-tiles (one per K-group) are consumed per barrier
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + ST * A_STAGE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kg = warp >> 2;           // K-group
+  const int w4 = warp & 3;
+  const int wm0 = (w4 >> 1) * 16, wn0 = (w4 & 1) * 32;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (p.K + BK - 1) / BK;
+  constexpr int A_CPR = BK / VEC, A_TOTAL = BM * A_CPR, NA = (A_TOTAL + NT - 1) / NT;
+  constexpr int B_CPR = BN / VEC, B_TOTAL = BK * B_CPR, NB_ = (B_TOTAL + NT - 1) / NT;
+  constexpr bool A_EXACT = (A_TOTAL % NT == 0), B_EXACT = (B_TOTAL % NT == 0);
+  const double* a_g[NA];
+  unsigned a_s[NA];
+  int a_kleft[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int id = tid + i * NT;
+    const int r = id / A_CPR, ck = (id % A_CPR) * VEC;
+    const int gr = m0 + r;
+    const bool used = A_EXACT || (id < A_TOTAL);
+    const bool ok = used && (gr < p.M);
+    a_g[i] = ok ? (p.A + (size_t)gr * p.lda + ck) : p.A;
+    a_s[i] = used ? smem_u32(As + r * A_LD + ck) : 0xffffffffu;
+    a_kleft[i] = ok ? (p.K - ck) : 0;
+  }
+  const double* b_g[NB_];
+  unsigned b_s[NB_];
+  int b_kr[NB_], b_cv[NB_];
+#pragma unroll
+  for (int i = 0; i < NB_; ++i) {
+    const int id = tid + i * NT;
+    const int r = id / B_CPR, cc = (id % B_CPR) * VEC;
+    const int gc = n0 + cc;
+    const bool used = B_EXACT || (id < B_TOTAL);
+    int cv = p.N - gc;
+    cv = cv < 0 ? 0 : (cv > VEC ? VEC : cv);
+    if (!used) cv = 0;
+    b_g[i] = cv > 0 ? (p.B + (size_t)r * p.ldb + gc) : p.B;
+    b_s[i] = used ? smem_u32(Bs + r * B_LD + cc) : 0xffffffffu;
+    b_kr[i] = r;
+    b_cv[i] = cv;
+  }
+  const size_t b_step = (size_t)BK * p.ldb;
+  const int a_frag = (wm0 + g) * A_LD + t;
+  const int b_frag = t * B_LD + wn0 + g;
+  const bool full = (VEC == 2) && (m0 + BM <= p.M) && (n0 + BN <= p.N) && (p.K % BK == 0);
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");  // T2 is produced by the preceding matvec_a grid
+
+  auto run = [&](auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    int kt_load = 0, st_load = 0;
+    auto issue = [&]() {
+      if (kt_load < KT) {
+        const unsigned aoff = st_load * (A_STAGE * 8), boff = st_load * (B_STAGE * 8);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          if (A_EXACT || a_s[i] != 0xffffffffu) {
+            if constexpr (FULL) {
+              cp16(a_s[i] + aoff, a_g[i]);
+            } else {
+              int valid = a_kleft[i];
+              valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+              const double* src = valid > 0 ? a_g[i] : p.A;
+              if constexpr (VEC == 2) cp16z(a_s[i] + aoff, src, valid * 8);
+              else cp8z(a_s[i] + aoff, src, valid * 8);
+              a_kleft[i] -= BK;
+            }
+            a_g[i] += BK;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NB_; ++i) {
+          if (B_EXACT || b_s[i] != 0xffffffffu) {
+            if constexpr (FULL) {
+              cp16(b_s[i] + boff, b_g[i]);
+            } else {
+              const int valid = (kt_load * BK + b_kr[i] < p.K) ? b_cv[i] : 0;
+              const double* src = valid > 0 ? b_g[i] : p.B;
+              if constexpr (VEC == 2) cp16z(b_s[i] + boff, src, valid * 8);
+              else cp8z(b_s[i] + boff, src, valid * 8);
+            }
+            b_g[i] += b_step;
+          }
+        }
+      }
+      cp_async_commit();
+      ++kt_load;
+      st_load = (st_load + 1 == ST) ? 0 : st_load + 1;
+    };
+#pragma unroll
+    for (int s = 0; s < ST - 2; ++s) issue();
+    int st_use = kg;  // stage of this K-group's tile in the current pair
+    for (int kt = 0; kt < KT; kt += 2) {
+      cp_async_wait<ST - 4>();
+      __syncthreads();
+      issue();
+      issue();
+      if (kt + kg < KT) {
+        const double* as = As + st_use * A_STAGE + a_frag;
+        const double* bs = Bs + st_use * B_STAGE + b_frag;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+          double a[2], b[4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a[i] = as[(i * 8) * A_LD + kk * 4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = bs[(kk * 4) * B_LD + j * 8];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      }
+      st_use = (st_use + 2 >= ST) ? st_use + 2 - ST : st_use + 2;
+    }
+    cp_async_wait<0>();
+  };
+  if (full) run(TrueT{});
+  else run(FalseT{});
+  __syncthreads();
+  // combine the two K-groups: group 1 parks its tile in shared memory, group 0 adds (fixed order) and stores
+  double* red = smem;  // [4 warps][2][4][32 lanes] double2
+  if (kg == 1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(red + (((w4 * 2 + i) * 4 + j) * 32 + lane) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+  }
+  __syncthreads();
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = m0 + wm0 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 o = *reinterpret_cast<const double2*>(red + (((w4 * 2 + i) * 4 + j) * 32 + lane) * 2);
+        const double v0 = acc[i][j][0] + o.x, v1 = acc[i][j][1] + o.y;
+        const int col = n0 + wn0 + j * 8 + 2 * t;
+        if (row < p.M && col < p.N) {
+          double* cp = p.C + (size_t)row * p.ldc + col;
+          if (VEC == 2 && col + 1 < p.N) *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+          else {
+            cp[0] = v0;
+            if (col + 1 < p.N) cp[1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int WL, int MI, int WM, int WN>
+constexpr size_t mva_smem() {
+  return (size_t)(STAGES * (WL * 8 * MI * WM * (BK + 4) + BK * (4 * 8 * WN + 4)) + 16 * WL * 8) * sizeof(double);
+}
+
+template <int WL, int MI, int WM, int WN, int VEC>
+void launch_mva(Ctx* ctx, const MvAArgs& a) {
+  auto kern = matvec_a_kernel<WL, MI, WM, WN, VEC>;
+  constexpr size_t smem = mva_smem<WL, MI, WM, WN>();
+  static bool configured = false;
+  if (!configured) {
+    QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.chil + 8 * MI * WM - 1) / (8 * MI * WM), (a.chir + 8 * WN - 1) / (8 * WN));
+  kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(a);
+  check_launch(ctx, "matvec_a");
+}
+
+int g_mva_shape = -1;  // QTT_MVA_SHAPE: tuning override (0: 8 warps 32x16, 1: 4 warps 16x16, 2: 4 warps MI=2 32x16)
+
+template <int WL, int VEC>
+void launch_mva_shape(Ctx* ctx, const MvAArgs& a) {
+  int shape = g_mva_shape;
+  if (shape < 0) {
+    // 8 warps (footprint 32 x 16) once that yields enough CTAs for most SMs; otherwise 4 warps (16 x 16)
+    const long big = (long)((a.chil + 31) / 32) * ((a.chir + 15) / 16);
+    shape = (big >= (long)(ctx->sms * 3) / 4) ? 0 : 1;
+  }
+  if (shape == 0) launch_mva<WL, 1, 4, 2, VEC>(ctx, a);
+  else if (shape == 1) launch_mva<WL, 1, 2, 2, VEC>(ctx, a);
+  else launch_mva<WL, 2, 2, 2, VEC>(ctx, a);
+}
+
+template <int VEC>
+void launch_mva_wl(Ctx* ctx, const MvAArgs& a) {
+  switch (a.wl) {
+    case 1: launch_mva_shape<1, VEC>(ctx, a); break;
+    case 2: launch_mva_shape<2, VEC>(ctx, a); break;
+    case 3: launch_mva_shape<3, VEC>(ctx, a); break;
+    case 4: launch_mva_shape<4, VEC>(ctx, a); break;
+    case 5: launch_mva_shape<5, VEC>(ctx, a); break;
+    case 6: launch_mva_shape<6, VEC>(ctx, a); break;
+    default: fail(QTT_ERR_UNSUPPORTED, "matvec2_fused: wl = %d", a.wl);
+  }
+}
+
+}  // namespace
+
+bool matvec2_fused_ok(int wl, int wr) { return wl >= 1 && wl <= 6 && wr >= 1 && wr <= 8; }
+
+size_t matvec2_fused_scratch(int chil, int chir, int wr) { return (size_t)4 * chil * chir * wr + 64; }
+
+void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R, const double* v, double* out, int chil, int chir,
+                   int wl, int wr, double* scratch) {
+  QTT_REQUIRE(matvec2_fused_ok(wl, wr), "matvec2_fused: MPO bond dimension out of range");
+  double* T2 = scratch;
+  MvAArgs a;
+  a.L = L; a.v = v; a.W12 = W12; a.T2 = T2;
+  a.chil = chil; a.chir = chir; a.wl = wl; a.wr = wr;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vecA = (chil % 2 == 0) && (chir % 2 == 0) && al16(L) && al16(v) && al16(T2);
+  if (g_mva_shape == -1 && getenv("QTT_MVA_SHAPE")) g_mva_shape = atoi(getenv("QTT_MVA_SHAPE"));
+  if (vecA) launch_mva_wl<2>(ctx, a);
+  else launch_mva_wl<1>(ctx, a);
+  MvBArgs b;
+  b.A = T2; b.B = R; b.C = out;
+  b.M = 4 * chil; b.N = chir; b.K = wr * chir;
+  b.lda = (long)wr * chir; b.ldb = chir; b.ldc = chir;
+  const bool vecB = (chir % 2 == 0) && al16(T2) && al16(R) && al16(out);
+  // the request is padded to > half of an SM's shared memory so that at most ONE matvec_b CTA is resident per SM: with
+  // programmatic dependent launch the early CTAs would otherwise pile up two-deep on the SMs that matvec_a leaves idle
+  constexpr size_t smemB_used = (size_t)6 * (32 * (BK + 4) + BK * (64 + 4)) * sizeof(double);
+  constexpr size_t smemB_max = smemB_used > 116 * 1024 ? smemB_used : 116 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    configured = true;
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((b.M + 31) / 32, (b.N + 63) / 64);
+    cfg.blockDim = dim3(256);
+    const long ctas_b = (long)((b.M + 31) / 32) * ((b.N + 63) / 64);
+    cfg.dynamicSmemBytes = ctas_b <= ctx->sms ? smemB_max : smemB_used;  // single wave: one CTA per SM (see above)
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool pdl = !(getenv("QTT_PDL") && atoi(getenv("QTT_PDL")) == 0);
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (vecB) QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<2>, b));
+    else QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<1>, b));
+  }
+  check_launch(ctx, "matvec_b");
+}
+
+}  // namespace qtt

@@ -12,6 +12,7 @@
 // GMRES scalars (Hessenberg column, Givens rotations, residual estimate, convergence flag) live in device memory and
 // are advanced by a one-thread kernel; the host polls a pinned, device-written flag to stop enqueuing early.
 #include "common.cuh"
+#include "krylov_scalars.cuh"
 #include <chrono>
 #include <functional>
 #include <cstdlib>
@@ -22,69 +23,11 @@ void kry_dots_acc(Ctx*, const double*, int, size_t, const double*, double*);
 
 namespace {
 
-constexpr int KD_MAX = 62;
+using namespace kscal;
 int g_trace_sweeps = 0;  // sweeps completed in this process (QTT_DUMP addresses a sweep by this count)
-// layout of the scalar block in ctx->d_scal (doubles)
-enum {
-  S_BETA = 0, S_NRES2 = 1, S_R0N2 = 2, S_DONE = 3, S_K = 4, S_NRES = 5, S_THETA = 6, S_TMP = 7,
-  OFF_H1 = 16, OFF_H2 = 16 + 64, OFF_Y = 16 + 128, OFF_GC = 16 + 192, OFF_GS = 16 + 256, OFF_YK = 16 + 320,
-  OFF_COEF = 16 + 384, OFF_R = 512, OFF_END = 512 + 64 * 64
-};
-// pinned host status block (ctx->h_scal + 64 ...)
-enum { H_DONE = 64, H_K = 65, H_BETA = 66, H_READ = 80 };
 
-__device__ __forceinline__ void givens(double f, double g, double& c, double& s, double& r) {
-  if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
-  if (f == 0.0) { c = 0.0; s = g > 0 ? 1.0 : -1.0; r = fabs(g); return; }
-  double h = hypot(f, g);
-  double sg = f > 0 ? 1.0 : -1.0;
-  c = fabs(f) / h;
-  s = sg * g / h;
-  r = sg * h;
-}
-
-// One Arnoldi step's scalar work (KrylovKit GMRES inner loop): fold the shift into the Hessenberg
-// column, apply the stored Givens rotations, create the new one, rotate the rhs, update the residual estimate.
 __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, double tol, int ld, volatile double* hstat) {
-  if (S[S_DONE] != 0.0) return;
-  double nres = sqrt(S[S_NRES2]);
-  S[S_NRES] = nres;
-  double* Rm = S + OFF_R;
-  double* y = S + OFF_Y;
-  double* gc = S + OFF_GC;
-  double* gs = S + OFF_GS;
-  if (k == 1) y[0] = sqrt(S[S_R0N2]);
-  double hn2 = nres * nres;
-  for (int i = 0; i < k; ++i) {
-    double h = S[OFF_H1 + i] + S[OFF_H2 + i];
-    hn2 += h * h;
-    Rm[i * ld + (k - 1)] = (i == k - 1) ? (a0 + a1 * h) : (a1 * h);
-  }
-  // Krylov space exhausted (invariant subspace): the next basis vector would be rounding noise
-  const bool breakdown = !(nres > 1e-13 * sqrt(hn2));
-  for (int i = 0; i < k - 1; ++i) {
-    double t1 = Rm[i * ld + (k - 1)], t2 = Rm[(i + 1) * ld + (k - 1)];
-    Rm[i * ld + (k - 1)] = gc[i] * t1 + gs[i] * t2;
-    Rm[(i + 1) * ld + (k - 1)] = -gs[i] * t1 + gc[i] * t2;
-  }
-  double c, s, r;
-  givens(Rm[(k - 1) * ld + (k - 1)], a1 * nres, c, s, r);
-  gc[k - 1] = c;
-  gs[k - 1] = s;
-  Rm[(k - 1) * ld + (k - 1)] = r;
-  double yk = y[k - 1];
-  y[k - 1] = c * yk;
-  y[k] = -s * yk;
-  double beta = fabs(y[k]);
-  S[S_BETA] = beta;
-  S[S_K] = (double)k;
-  if (!(beta > tol) || breakdown) S[S_DONE] = 1.0;
-  if (hstat) {
-    hstat[H_K] = (double)k;
-    hstat[H_BETA] = beta;
-    hstat[H_DONE] = S[S_DONE];
-    __threadfence_system();
-  }
+  gmres_step_scalars(S, k, a0, a1, tol, ld, hstat);
 }
 
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
@@ -155,6 +98,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
   double* S = ctx->d_scal;
   volatile double* hstat = ctx->h_scal;
   auto vec = [&](int i) { return ws.V + (size_t)i * len; };
+  const bool fused = kry_cgs2_fused_ok(ctx, len);
   mv(x, ws.w);
   st.matvecs++;
   kry_axpby(ctx, len, 1.0, beff, -a0, x, -a1, ws.w, ws.r);
@@ -178,13 +122,21 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
     for (k = 1; k <= kd; ++k) {
       mv(vec(k - 1), ws.w);
       st.matvecs++;
-      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
-      kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
-      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
-      kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
-      gmres_update_kernel<<<1, 1, 0, ctx->stream>>>(S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
-      check_launch(ctx, "gmres_update");
-      kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
+      if (fused) {
+        // one cooperative launch: CGS2, norm, Hessenberg/Givens update, v_k = w / |w|.  v_k is zeroed by the done flag of
+        // the PREVIOUS step: at the step that sets the flag the vector is still finite (|w| != 0, entries <= |w|), its
+        // coefficient is zero, and every later vector is written as zeros.
+        kry_cgs2_fused(ctx, ws.V, k, len, ws.w, vec(k), S, OFF_H1, OFF_H2, S_NRES2, S_DONE, 1, a0, a1, fixed ? -1.0 : tol,
+                       fixed ? nullptr : ctx->h_scal);
+      } else {
+        kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
+        kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
+        kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
+        kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
+        gmres_update_kernel<<<1, 1, 0, ctx->stream>>>(S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
+        check_launch(ctx, "gmres_update");
+        kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
+      }
       if (!fixed && hstat[H_DONE] != 0.0) break;
     }
     int kfin = kd;
@@ -222,22 +174,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
 // ---- Lanczos with full (CGS2) orthogonalisation: local eigen solve of the Krylov `dmrg_target` variant ------------
 // Projected matrix T (k x k, symmetric) is accumulated on the device; its eigen-decomposition (k <= 62) is done by a
 // single-warp cyclic Jacobi kernel; the Ritz vector nearest `target` is assembled with one multi-axpy.
-__global__ void lanczos_store_col_kernel(double* S, int k, int ld) {
-  // column k-1 of the projected matrix from the CGS2 coefficients; subdiagonal = residual norm
-  if (S[S_DONE] != 0.0) return;
-  double* T = S + OFF_R;
-  double nres = sqrt(S[S_NRES2]);
-  double hn2 = nres * nres;
-  for (int i = 0; i < k; ++i) {
-    double h = S[OFF_H1 + i] + S[OFF_H2 + i];
-    hn2 += h * h;
-    T[i * ld + (k - 1)] = h;
-    T[(k - 1) * ld + i] = h;
-  }
-  S[S_NRES] = nres;
-  S[S_K] = (double)k;
-  if (!(nres > 1e-13 * sqrt(hn2))) S[S_DONE] = 1.0;  // invariant subspace: stop expanding (KrylovKit: normres <= tol)
-}
+__global__ void lanczos_store_col_kernel(double* S, int k, int ld) { lanczos_step_scalars(S, k, ld); }
 
 __global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, double target, double* ritz_coef) {
   const int k = (int)S[S_K];
@@ -313,6 +250,7 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
                    KrylovWork& ws, LocalStats& st) {
   double* S = ctx->d_scal;
   auto vec = [&](int i) { return ws.V + (size_t)i * len; };
+  const bool fused = kry_cgs2_fused_ok(ctx, len);
   for (int it = 0; it < maxiter; ++it) {
     kry_nrm2sq(ctx, x, len, S + S_R0N2);
     set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
@@ -322,13 +260,17 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
     for (int k = 1; k <= kd; ++k) {
       mv(vec(k - 1), ws.w);
       st.matvecs++;
-      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
-      kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
-      kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
-      kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
-      lanczos_store_col_kernel<<<1, 1, 0, ctx->stream>>>(S, k, 64);
-      check_launch(ctx, "lanczos_store_col");
-      if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
+      if (fused) {
+        kry_cgs2_fused(ctx, ws.V, k, len, ws.w, k < kd ? vec(k) : nullptr, S, OFF_H1, OFF_H2, S_NRES2, S_DONE, 2, 0.0, 0.0, 0.0, nullptr);
+      } else {
+        kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H1);
+        kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
+        kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
+        kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
+        lanczos_store_col_kernel<<<1, 1, 0, ctx->stream>>>(S, k, 64);
+        check_launch(ctx, "lanczos_store_col");
+        if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
+      }
     }
     {
       constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);

@@ -77,7 +77,7 @@ def test_env_updates_match_oracle(lib, dims):
     assert rel(Rn, O.env_right_update(R, x, W)) < 1e-13
 
 
-@pytest.mark.parametrize("nvec,ln", [(1, 64), (5, 1000), (30, 4096), (31, 65536), (7, 333)])
+@pytest.mark.parametrize("nvec,ln", [(1, 64), (5, 1000), (30, 4096), (31, 65536), (7, 333), (30, 262144), (3, 8)])
 def test_krylov_ops(lib, nvec, ln):
     rng = np.random.default_rng(nvec + ln)
     V = rng.standard_normal((nvec, ln)); w = rng.standard_normal(ln)
@@ -92,6 +92,14 @@ def test_krylov_ops(lib, nvec, ln):
     wo, hh, nrm, _ = lib.krylov_op(3, Q, w)
     assert np.abs(Q @ wo).max() < 1e-13 * np.linalg.norm(w)
     assert rel(hh, Q @ w) < 1e-12 and abs(nrm - np.linalg.norm(wo)) < 1e-12 * nrm
+    if ln % 2 == 0:
+        # the fused single-launch CGS2 Arnoldi step (op 4) returns the same coefficients, remainder and norm
+        wf, hf, nf, _ = lib.krylov_op(4, Q, w)
+        assert np.abs(Q @ wf).max() < 1e-13 * np.linalg.norm(w)
+        assert rel(hf, Q @ w) < 1e-12 and abs(nf - np.linalg.norm(wf)) < 1e-12 * nf
+        assert rel(wf, wo) < 1e-12
+        wf2, hf2, nf2, _ = lib.krylov_op(4, Q, w)   # bit-reproducible: fixed-order reductions
+        assert np.array_equal(wf, wf2) and np.array_equal(hf, hf2) and nf == nf2
 
 
 @pytest.mark.parametrize("ortho", ["left", "right"])

@@ -34,9 +34,9 @@ if "krylov" in what:
     ln = 4 * chi * chi
     for nvec in (1, 8, 16, 30):
         V = rng.standard_normal((nvec, ln)); wv = rng.standard_normal(ln)
-        for op, nm in ((0, "dots"), (1, "axpys"), (3, "cgs2")):
+        for op, nm in ((0, "dots"), (1, "axpys"), (3, "cgs2"), (4, "cgs2_fused")):
             _, _, _, ms = q.krylov_op(op, V, wv, h=np.ones(nvec) * 1e-3, reps=100)
-            passes = {0: 1, 1: 1, 3: 4}[op]
+            passes = {0: 1, 1: 1, 3: 4, 4: 4}[op]
             print(json.dumps({"krylov": nm, "nvec": nvec, "len": ln, "ms": ms, "GBps_alg": passes * (nvec + 1) * ln * 8 / ms * 1e-6}))
 if "split" in what:
     # graded spectrum like a converged two-site tensor, and a flat random one
