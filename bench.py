@@ -156,6 +156,7 @@ def run_ours(args):
     x = dx
     for i in range(args.warmup):
         x, info = step(x, canonical=True)   # random_mps() is right-orthonormal by construction
+    x_start = x.clone() if hasattr(x, "clone") else x
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -192,26 +193,32 @@ def run_ours(args):
     L = rng.standard_normal((chi, 3, chi)); R = rng.standard_normal((chi, 3, chi))
     W = A[1]
     v = rng.standard_normal((chi, 2, 2, chi))
-    _, mv_ms = q.matvec2(L, W, W, R, v, reps=200, ctx=ctx)
+    _, mv_ms = q.matvec2(L, W, W, R, v, reps=args.roofline_reps, ctx=ctx)
     f_mv = q.matvec2_flops(chi, chi, 3, 3, 3)
     achieved = f_mv / (mv_ms * 1e-3) / 1e12
     sweep_mv_tflops = infos[-1]["flops_matvec"] / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
-                "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 (gemm_dmma_kernel x2 + apply_w12 + sum_partials)" % chi,
+                "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_kernel (L.v DMMA GEMM + W12 register epilogue) + "
+                          "matvec_b_kernel (T2.R DMMA GEMM, in-CTA split-K), the pair timed back to back with CUDA events on "
+                          "the library's stream" % chi,
+                "share_of_step": infos[-1]["matvecs"] * mv_ms / ms_per_step,
                 "flops_per_launch": f_mv, "ms_per_launch": mv_ms,
                 "peak_source": "measured FP64 DMMA.8x8x4 issue rate on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak_dmma_dfma.txt); "
                                "MEASURED_PEAKS.json carries no FP64 entry",
                 "matvec_tflops_inside_sweep_incl_krylov_svd_env": sweep_mv_tflops}
     # ---- e2e: host buffers -> upload -> one sweep -> download
-    hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x0)
-    e2e_steps = max(1, min(args.steps, 2))
+    # the e2e input is the state the timed steps started from (same per-sweep work as `value`), downloaded once
+    # outside the timed region and re-homed in pinned memory
+    hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x_start.download())
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    xo = hx
     for i in range(e2e_steps):
         xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
                            x0_canonical=True, ctx=ctx, return_info=True)
-    e2e_t = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = (time.perf_counter() - t0) / max(e2e_steps, 1)
     h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)
     d2h = sum(c.nbytes for c in xo)
     out = {
@@ -224,7 +231,10 @@ def run_ours(args):
                    "instances": world, "l2": "256 MB buffer written between timed steps (L2 flush)",
                    "wall_s_timed_region": wall},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": ({"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                 "note": "upload of A, b, x (pinned host cores) + one sweep + download of x, per step, through "
+                         "the public linsolve() call; x = the state the timed device-resident steps started from"}
+                if e2e_steps else None),
         "roofline": roofline,
         "sweep": {"matvec_flops_per_sweep": flops_sweep, "maxlinkdim": int(infos[-1]["maxlinkdim"]),
                   "svd_sweeps_max": int(infos[-1]["svd_sweeps_max"]), "solver_resid_max_over_ranks": float(allt[:, 2].max())},
@@ -298,6 +308,8 @@ def main():
     ap.add_argument("--krylov", type=int, default=KRYLOV)
     ap.add_argument("--cpu-bonds", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list runs)")
+    ap.add_argument("--roofline-reps", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,94 @@
+"""Multi-GPU batching of INDEPENDENT instances.
+
+A single two-site sweep is sequential (bond b+1 needs bond b's new core and environment), so one solve stays on one
+GPU.  What shards naturally is a batch of independent solves (Helmholtz wavenumber sweeps, many right-hand sides,
+many DFT inputs -- reference drivers examples/helmholtz_equation/helmholtz_equation.jl:153-224 loop over them
+serially): instance i is owned by rank i mod world, every rank runs one process + one `qtt_ctx` on its GPU, there is
+no collective on the data path, and `torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests) only
+gathers the per-instance scalars (residual, matvec count, seconds) and, on request, the result cores to rank 0.
+"""
+import time
+
+import numpy as np
+
+__all__ = ["shard_instances", "batch_solve", "batch_linsolve"]
+
+
+def shard_instances(n_instances, rank, world):
+    """Static round-robin partition: identical cost per instance at fixed chi, so no load balancer is needed."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    return list(range(rank, n_instances, world))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def batch_solve(n_instances, solve_one, *, gather_results=False, device=None):
+    """Runs `solve_one(i) -> (result, scalars)` for the instances this rank owns and gathers the scalars everywhere.
+
+    scalars: 1-D sequence of floats of a fixed length m (e.g. residual, matvecs, seconds).
+    Returns (table, results): table is an (n_instances, m) float64 array identical on every rank; results maps
+    instance id -> result for the owned instances (all instances on rank 0 when gather_results)."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    mine = shard_instances(n_instances, rank, world)
+    results, rows = {}, []
+    for i in mine:
+        res, sc = solve_one(i)
+        results[i] = res
+        rows.append([float(i)] + [float(v) for v in sc])
+    m = len(rows[0]) if rows else None
+    if dist:
+        # the row width is agreed first (a rank may own no instance when n_instances < world)
+        wt = torch.tensor([m or 0], dtype=torch.int64, device=device)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        m = int(wt.item())
+    if not m:
+        return np.zeros((0, 0)), results
+    per = (n_instances + world - 1) // world
+    local = torch.full((per, m), float("nan"), dtype=torch.float64, device=device)
+    if rows:
+        local[: len(rows)] = torch.tensor(rows, dtype=torch.float64, device=device)
+    if dist:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)     # NCCL on the GPU box: scalars only, << 1 % of the run time
+        allrows = torch.cat(parts).cpu().numpy()
+    else:
+        allrows = local.cpu().numpy()
+    table = np.full((n_instances, m - 1), np.nan)
+    for r in allrows:
+        if not np.isnan(r[0]):
+            table[int(r[0])] = r[1:]
+    if gather_results and dist and world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(results, gathered, dst=0)
+        if rank == 0:
+            results = {k: v for part in gathered for k, v in part.items()}
+    return table, results
+
+
+def batch_linsolve(instances, *, ctx=None, gather_results=False, device=None, **kw):
+    """`linsolve` over a batch: instances[i] = (A, b, x0, a0, a1) as host cores (or Device* handles for A / b shared by
+    many instances).  Per-instance scalars: sqeuclidean_normalized residual, matvecs, seconds.  Keyword arguments are
+    those of `linsolve` (nsweeps, maxdim, cutoff, tol, krylovdim, maxiter, ...)."""
+    from .api import linsolve, sqeuclidean_normalized
+    from ._lib import default_context
+    ctx = ctx or default_context()
+
+    def solve_one(i):
+        A, b, x0, a0, a1 = instances[i]
+        t0 = time.perf_counter()
+        x, info = linsolve(A, b, x0, a0, a1, ctx=ctx, return_info=True, **kw)
+        dt = time.perf_counter() - t0
+        if a0 == 0 and a1 == 1:
+            res = sqeuclidean_normalized((A, x), b, ctx=ctx)
+        else:
+            res = max(i_["solver_resid"] for i_ in info)  # shifted system: report the local solver's residual estimate
+        return x, (res, sum(i_["matvecs"] for i_ in info), dt)
+
+    return batch_solve(len(instances), solve_one, gather_results=gather_results, device=device)

@@ -8,3 +8,4 @@ from ._lib import *        # noqa: F401,F403,E402
 from .chains import *      # noqa: F401,F403,E402
 from .operators import *   # noqa: F401,F403,E402
 from .api import *         # noqa: F401,F403,E402
+from .batch import *     # noqa: F401,F403,E402

@@ -1,0 +1,281 @@
+# ITensorQTTB200.jl -- the reference-side binding of libqtt_b200.so (include/qtt_b200.h).
+#
+# Drop-in for ONE hot path of ITensorQTT: `linsolve(A, b, x0, a0, a1; nsweeps, maxdim, cutoff, ...)`,
+# `dmrg_target`, `apply_dft_mpo` / `apply_idft_mpo`, `prolongate`, `retract` keep their signatures
+# (reference examples/airy_equation/src/linsolve.jl:24-34, src/dmrg_target.jl:1-12, src/dft.jl:121-133,
+# src/prolongation.jl:29-45,70-90); the two-site sweep / MPO.MPS apply run on a B200 through `ccall`.
+# Only dense column-major arrays and shapes cross the boundary: Index identity, tags, prime levels and the
+# `reverse` / output-bit relabelling of src/dft.jl:76-79,124 stay on the Julia side.
+#
+# NOTE: Julia is not installed in the build container, so this file is written against the C header and the
+# ITensors API but has not been executed there; the same ABI is exercised from Python `ctypes` by the test-suite.
+module ITensorQTTB200
+
+using ITensors
+using ITensorQTT: dft_mpo, idft_mpo, prolongation_mpo, siteinds_per_dimension
+
+const libqtt = get(ENV, "LIBQTT_B200", "libqtt_b200.so")
+
+# ---- mirror of the C structs (field order and types as in include/qtt_b200.h) ------------------------------
+struct QttSweepParams
+  nsweeps::Int32
+  maxdim::Ptr{Int32}
+  mindim::Ptr{Int32}
+  cutoff::Ptr{Float64}
+  solver::Int32
+  a0::Float64
+  a1::Float64
+  tol::Float64
+  krylovdim::Int32
+  maxiter::Int32
+  fixed_matvecs::Int32
+  normalize::Int32
+  outputlevel::Int32
+  target::Float64
+  svd_max_sweeps::Int32
+  x0_canonical::Int32
+end
+
+struct QttSweepInfo
+  maxlinkdim::Int32
+  svd_sweeps_max::Int32
+  maxtruncerr::Float64
+  seconds::Float64
+  solver_resid::Float64
+  matvecs::Int64
+  flops_matvec::Float64
+  t_matvec::Float64
+  t_env::Float64
+  t_svd::Float64
+  t_krylov::Float64
+  energy::Float64
+  device_ms::Float64
+end
+
+const QTT_SOLVER_GMRES = Int32(0)
+const QTT_SOLVER_LANCZOS = Int32(1)
+
+struct QttError <: Exception
+  code::Int
+  msg::String
+end
+
+mutable struct Context
+  handle::Ptr{Cvoid}
+  function Context(device::Integer=0)
+    h = ccall((:qtt_ctx_create, libqtt), Ptr{Cvoid}, (Cint,), device)
+    h == C_NULL && throw(QttError(-2, unsafe_string(ccall((:qtt_global_error, libqtt), Cstring, ()))))
+    ctx = new(h)
+    finalizer(c -> ccall((:qtt_ctx_destroy, libqtt), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+    return ctx
+  end
+end
+
+const default_ctx = Ref{Union{Nothing,Context}}(nothing)
+context() = something(default_ctx[], (default_ctx[] = Context(0)))
+
+function check(ctx::Context, rc::Integer)
+  rc == 0 && return nothing
+  throw(QttError(rc, unsafe_string(ccall((:qtt_last_error, libqtt), Cstring, (Ptr{Cvoid},), ctx.handle))))
+end
+
+# process_sweeps semantics of tdvp: scalars or per-sweep vectors, last value repeated
+sweepvec(::Type{T}, v::Number, n) where {T} = fill(T(v), n)
+sweepvec(::Type{T}, v::AbstractVector, n) where {T} = T[v[min(i, length(v))] for i in 1:n]
+
+# ---- chains: ITensors -> dense column-major cores ------------------------------------------------------------
+# MPS core j as array(x[j], l_{j-1}, s_j, l_j) with size-1 dummy links at the ends
+function mps_cores(x::MPS)
+  n = length(x)
+  cores = Vector{Array}(undef, n)
+  chi = ones(Int64, n + 1)
+  for j in 1:n
+    s = siteind(x, j)
+    l = j > 1 ? linkind(x, j - 1) : nothing
+    r = j < n ? linkind(x, j) : nothing
+    is = filter(!isnothing, (l, s, r))
+    a = array(x[j], is...)
+    dl = isnothing(l) ? 1 : dim(l)
+    dr = isnothing(r) ? 1 : dim(r)
+    cores[j] = reshape(a, dl, 2, dr)
+    chi[j] = dl
+    chi[j + 1] = dr
+  end
+  return cores, chi
+end
+
+# MPO core j as array(A[j], l, r, s, s')  (index order of reference src/laplacian.jl:32)
+function mpo_cores(A::MPO)
+  n = length(A)
+  cores = Vector{Array}(undef, n)
+  w = ones(Int64, n + 1)
+  for j in 1:n
+    s = siteind(A, j; plev=0)
+    l = j > 1 ? linkind(A, j - 1) : nothing
+    r = j < n ? linkind(A, j) : nothing
+    is = filter(!isnothing, (l, r, s, s'))
+    a = array(A[j], is...)
+    dl = isnothing(l) ? 1 : dim(l)
+    dr = isnothing(r) ? 1 : dim(r)
+    cores[j] = reshape(a, dl, dr, 2, 2)
+    w[j] = dl
+    w[j + 1] = dr
+  end
+  return cores, w
+end
+
+dtype_code(cores) = any(c -> eltype(c) <: Complex, cores) ? Cint(1) : Cint(0)
+
+function upload(ctx::Context, x::MPS)
+  cores, chi = mps_cores(x)
+  T = dtype_code(cores) == 1 ? ComplexF64 : Float64
+  cores = [convert(Array{T,3}, c) for c in cores]
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve cores begin
+    ptrs = [Ptr{Cvoid}(pointer(c)) for c in cores]
+    check(ctx, ccall((:qtt_mps_upload, libqtt), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cvoid}}),
+                     ctx.handle, length(cores), chi, ptrs, dtype_code(cores), out))
+  end
+  return out[]
+end
+
+function upload(ctx::Context, A::MPO)
+  cores, w = mpo_cores(A)
+  T = dtype_code(cores) == 1 ? ComplexF64 : Float64
+  cores = [convert(Array{T,4}, c) for c in cores]
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve cores begin
+    ptrs = [Ptr{Cvoid}(pointer(c)) for c in cores]
+    check(ctx, ccall((:qtt_mpo_upload, libqtt), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cvoid}}),
+                     ctx.handle, length(cores), w, ptrs, dtype_code(cores), out))
+  end
+  return out[]
+end
+
+# device chain -> MPS on the given site indices with fresh link indices
+function download(ctx::Context, h::Ptr{Cvoid}, sites::Vector{<:Index})
+  n = ccall((:qtt_mps_length, libqtt), Cint, (Ptr{Cvoid},), h)
+  chi = Vector{Int64}(undef, n + 1)
+  check(ctx, ccall((:qtt_mps_dims, libqtt), Cint, (Ptr{Cvoid}, Ptr{Int64}), h, chi))
+  T = ccall((:qtt_mps_dtype, libqtt), Cint, (Ptr{Cvoid},), h) == 1 ? ComplexF64 : Float64
+  cores = [Array{T,3}(undef, chi[j], 2, chi[j + 1]) for j in 1:n]
+  GC.@preserve cores begin
+    ptrs = [Ptr{Cvoid}(pointer(c)) for c in cores]
+    check(ctx, ccall((:qtt_mps_download, libqtt), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), h, ptrs))
+  end
+  links = [Index(chi[j + 1], "Link,l=$j") for j in 1:(n - 1)]
+  ts = Vector{ITensor}(undef, n)
+  for j in 1:n
+    if n == 1
+      ts[j] = itensor(reshape(cores[j], 2), sites[j])
+    elseif j == 1
+      ts[j] = itensor(reshape(cores[j], 2, chi[2]), sites[j], links[1])
+    elseif j == n
+      ts[j] = itensor(reshape(cores[j], chi[n], 2), links[n - 1], sites[j])
+    else
+      ts[j] = itensor(cores[j], links[j - 1], sites[j], links[j])
+    end
+  end
+  return MPS(ts)
+end
+
+free_mps(h) = ccall((:qtt_mps_free, libqtt), Cvoid, (Ptr{Cvoid},), h)
+free_mpo(h) = ccall((:qtt_mpo_free, libqtt), Cvoid, (Ptr{Cvoid},), h)
+
+# ---- the drop-in entry points ---------------------------------------------------------------------------------
+"""
+    linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, mindim, cutoff, tol, krylovdim, maxiter, ishermitian)
+
+Same signature and defaults as the reference (examples/airy_equation/src/linsolve.jl:24-34): solves (a0 + a1 A) x = b
+by two-site sweeps with a local GMRES, on the GPU.
+"""
+function linsolve(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; nsweeps, maxdim=typemax(Int32), mindim=1,
+                  cutoff=1e-16, tol=1e-5, krylovdim=20, maxiter=10, ishermitian=false, normalize=false, outputlevel=0,
+                  ctx::Context=context())
+  (a0 isa Real && a1 isa Real) || error("libqtt_b200: complex a0/a1 are not supported by this build")
+  hA = upload(ctx, A); hb = upload(ctx, b); hx = upload(ctx, x0)
+  md = sweepvec(Int32, min.(maxdim, typemax(Int32)), nsweeps)
+  mn = sweepvec(Int32, mindim, nsweeps)
+  co = sweepvec(Float64, cutoff, nsweeps)
+  infos = Vector{QttSweepInfo}(undef, nsweeps)
+  try
+    GC.@preserve md mn co begin
+      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), QTT_SOLVER_GMRES, a0, a1, tol, krylovdim, maxiter,
+                             0, normalize, outputlevel, 0.0, 0, 0))
+      check(ctx, ccall((:qtt_linsolve, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{QttSweepParams}, Ptr{QttSweepInfo}),
+                       ctx.handle, hA, hb, hx, p, infos))
+    end
+    return download(ctx, hx, siteinds(x0))
+  finally
+    free_mps(hx); free_mps(hb); free_mpo(hA)
+  end
+end
+
+"""
+    dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim, cutoff, ...)
+
+Reference src/dmrg_target.jl:1-12 with the Krylov local solver sketched at :14-21 (the dense `eigen` of the
+(4 chi^2)^2 effective operator does not exist beyond chi ~ 64).
+"""
+function dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim=typemax(Int32), mindim=1, cutoff=1e-16, tol=1e-12,
+                     krylovdim=30, maxiter=1, outputlevel=0, ctx::Context=context())
+  hA = upload(ctx, A); hx = upload(ctx, psi0)
+  md = sweepvec(Int32, min.(maxdim, typemax(Int32)), nsweeps)
+  mn = sweepvec(Int32, mindim, nsweeps)
+  co = sweepvec(Float64, cutoff, nsweeps)
+  infos = Vector{QttSweepInfo}(undef, nsweeps)
+  try
+    GC.@preserve md mn co begin
+      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), QTT_SOLVER_LANCZOS, 0.0, 1.0, tol, krylovdim, maxiter,
+                             0, 1, outputlevel, target_eigenvalue, 0, 0))
+      check(ctx, ccall((:qtt_dmrg_target, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{QttSweepParams}, Ptr{QttSweepInfo}),
+                       ctx.handle, hA, hx, p, infos))
+    end
+    return infos[end].energy, download(ctx, hx, siteinds(psi0))
+  finally
+    free_mps(hx); free_mpo(hA)
+  end
+end
+
+# `apply(A, psi; cutoff, maxdim, mindim)` (density-matrix algorithm); output on `noprime` of A's primed site indices
+function apply_mpo(A::MPO, psi::MPS; cutoff=1e-13, maxdim=0, mindim=1, ctx::Context=context())
+  hA = upload(ctx, A); hp = upload(ctx, psi)
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  try
+    check(ctx, ccall((:qtt_apply, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                     ctx.handle, hA, hp, cutoff, maxdim, mindim, out))
+    return download(ctx, out[], siteinds(psi))
+  finally
+    out[] != C_NULL && free_mps(out[]); free_mps(hp); free_mpo(hA)
+  end
+end
+
+# reference src/dft.jl:121-133: the chain reversal stays here
+function apply_dft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
+  s = siteinds(psi)
+  F = dft_mpo(s; cutoff)
+  phi = apply_mpo(F, psi; cutoff, kwargs...)
+  return MPS(reverse([phi[j] for j in 1:length(phi)]))
+end
+
+function apply_idft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
+  s = siteinds(psi)
+  F = idft_mpo(s; cutoff)
+  phi = apply_mpo(F, psi; cutoff, kwargs...)
+  return MPS(reverse([phi[j] for j in 1:length(phi)]))
+end
+
+# residual metric of reference src/mps_utils.jl:109-116
+function sqeuclidean_normalized(A::MPO, x::MPS, b::MPS; ctx::Context=context())
+  hA = upload(ctx, A); hx = upload(ctx, x); hb = upload(ctx, b)
+  sq = Ref{Float64}(0.0); sqn = Ref{Float64}(0.0)
+  try
+    check(ctx, ccall((:qtt_residual, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                     ctx.handle, hA, hx, hb, sq, sqn))
+    return sqn[]
+  finally
+    free_mps(hb); free_mps(hx); free_mpo(hA)
+  end
+end
+
+end # module
