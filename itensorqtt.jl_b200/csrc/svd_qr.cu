@@ -17,6 +17,7 @@
 //   3. descending sort of sigma^2, NDTensors.truncate! rule, gather of the kept rows.
 // Everything is enqueued without a host round trip; only the kept rank is read back at the end.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace qtt {
 namespace {
@@ -676,6 +677,13 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     qr_next_panel_kernel<<<1, 1, 0, ctx->stream>>>(ctl);
     check_launch(ctx, "qr_next_panel");
   }
+  const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
+  cudaEvent_t evq = nullptr, evj = nullptr;
+  if (trace) {
+    cudaEventCreate(&evq);
+    cudaEventCreate(&evj);
+    cudaEventRecord(evq, ctx->stream);
+  }
   {
     dim3 grid((q + p + 31) / 32, (kmax + 31) / 32);
     build_y_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(SE, q, p, ldp, qd, ldy, Y, ctl);
@@ -711,6 +719,15 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   QTT_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   QTT_CUDA(cudaMemcpyAsync(h_err, derr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (trace) {
+    cudaEventRecord(evj, ctx->stream);
+    cudaEventSynchronize(evj);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evq, evj);
+    fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: numerical rank %d, jacobi %d sweeps %.3f ms (after QR)\n", q, p, h_info[3], h_info[1], ms);
+    cudaEventDestroy(evq);
+    cudaEventDestroy(evj);
+  }
   RowSvd res;
   res.k = h_info[0];
   res.sweeps = h_info[1];
