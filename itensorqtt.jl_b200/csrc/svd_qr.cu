@@ -18,6 +18,7 @@
 // Everything is enqueued without a host round trip; only the kept rank is read back at the end.
 #include "common.cuh"
 #include <cstdlib>
+#include <string>
 
 namespace qtt {
 namespace {
@@ -588,6 +589,183 @@ __global__ void __launch_bounds__(64) jacobi_qr_kernel(JqArgs a) {
   }
 }
 
+// ---- two warps per row pair (row parts <= 512 doubles) ------------------------------------------------------------
+// A pair slot is served by TWO warps: warp A owns the R part of the two rows (dot products, rotation angle), warp B the
+// carried Q^T part (loaded while A reduces), which halves the per-warp load/store time of a round (a round is latency
+// bound: 3.3 us with one warp per 1024-double row pair, measured).  Rounds are separated by the grid barrier.
+// A point-to-point variant (each slot waits only for its two neighbour slots through release/acquire flags, which is
+// all the round-robin data flow requires) was measured SLOWER than the grid barrier on B200 (random 512 x 512:
+// 42-57 ms vs 23 ms) and was dropped.
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
+template <int NC>
+__global__ void __launch_bounds__(128) jacobi_qr_pair_kernel(JqArgs a) {
+  __shared__ double cs_s[2][4];  // per slot-unit: c, s, rotate?
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int unit_in_cta = warp >> 1;
+  const int role = warp & 1;  // 0: R part (angles), 1: carried part
+  const int units = gridDim.x * 2;
+  const int unit = blockIdx.x * 2 + unit_in_cta;
+  const int q = a.ctl->r;
+  const double thr = a.ctl->thr;
+  const int qe = (q + 1) & ~1;
+  const int npairs = qe / 2, rounds = qe - 1;
+  const int c_lo = role == 0 ? 0 : a.ndot;
+  const int c_hi = role == 0 ? a.ndot : a.ld;
+  unsigned target = 0;
+  int sweeps = 0;
+  int converged = (q < 2) ? 1 : 0;
+  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
+    bool rotated = false;
+    for (int r = 0; r < rounds; ++r) {
+      for (int i = unit; i < npairs; i += units) {
+        int ia, ib;
+        if (i == 0) {
+          ia = r;
+          ib = qe - 1;
+        } else {
+          ia = (r + i) % (qe - 1);
+          ib = (r - i + (qe - 1)) % (qe - 1);
+        }
+        if (ia > ib) {
+          int tmp = ia;
+          ia = ib;
+          ib = tmp;
+        }
+        const bool live = (ia < q && ib < q);
+        if (live) {
+          double* ra = a.Y + (size_t)ia * a.ld + c_lo;
+          double* rb = a.Y + (size_t)ib * a.ld + c_lo;
+          const int len = c_hi - c_lo;
+          double2 za[NC], zb[NC];
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            const int col = 2 * lane + 64 * k;
+            if (col < len) {
+              za[k] = __ldcg(reinterpret_cast<const double2*>(ra + col));
+              zb[k] = __ldcg(reinterpret_cast<const double2*>(rb + col));
+            } else {
+              za[k] = make_double2(0.0, 0.0);
+              zb[k] = make_double2(0.0, 0.0);
+            }
+          }
+          if (role == 0) {
+            double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              alpha += za[k].x * za[k].x + za[k].y * za[k].y;
+              beta += zb[k].x * zb[k].x + zb[k].y * zb[k].y;
+              gamma += za[k].x * zb[k].x + za[k].y * zb[k].y;
+            }
+            alpha = warp_sum(alpha);
+            beta = warp_sum(beta);
+            gamma = warp_sum(gamma);
+            double c = 1.0, s = 0.0, rot = 0.0;
+            if ((alpha > thr) && (beta > thr)) {
+              const double lim = sqrt(alpha) * sqrt(beta);
+              if ((lim > 0.0) && (fabs(gamma) > a.tol * lim)) {
+                jrotation(alpha, beta, gamma, c, s);
+                rot = 1.0;
+              }
+            }
+            if (lane == 0) {
+              cs_s[unit_in_cta][0] = c;
+              cs_s[unit_in_cta][1] = s;
+              cs_s[unit_in_cta][2] = rot;
+            }
+          }
+          pair_bar(1 + unit_in_cta);
+          const double c = cs_s[unit_in_cta][0], s = cs_s[unit_in_cta][1];
+          const bool rot = cs_s[unit_in_cta][2] != 0.0;
+          if (rot) {
+            rotated = true;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              const int col = 2 * lane + 64 * k;
+              if (col < len) {
+                __stcg(reinterpret_cast<double2*>(ra + col), make_double2(c * za[k].x - s * zb[k].x, c * za[k].y - s * zb[k].y));
+                __stcg(reinterpret_cast<double2*>(rb + col), make_double2(s * za[k].x + c * zb[k].x, s * za[k].y + c * zb[k].y));
+              }
+            }
+          }
+          if (npairs > units) pair_bar(1 + unit_in_cta);  // cs_s is reused by this unit's next slot of the round
+        }
+      }
+      grid_sync(a.sync, target);
+    }
+    if (rotated && lane == 0 && role == 0) atomicAdd(a.sync + 2 + sw, 1u);
+    grid_sync(a.sync, target);
+    sweeps = sw + 1;
+    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
+  }
+  const int gw = blockIdx.x * 4 + warp;
+  const int GW = gridDim.x * 4;
+  // sigma_i^2 = |R part of row i|^2
+  for (int i = gw; i < q; i += GW) {
+    const double* ri = a.Y + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ndot; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (!(acc > thr)) acc = 0.0;
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
+    if (i < q) {
+      const double ni = __ldcg(a.norms + i);
+      int rank = 0;
+      for (int j = 0; j < q; ++j) {
+        const double nj = __ldcg(a.norms + j);
+        rank += (nj > ni) || (nj == ni && j < i);
+      }
+      a.perm[rank] = i;
+      a.sig2[rank] = ni;
+    } else {
+      a.perm[i] = -1;
+      a.sig2[i] = 0.0;
+    }
+  }
+  grid_sync(a.sync, target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int len = a.kmax;
+    int n = len;
+    double err = 0.0;
+    int maxdim = a.maxdim < len ? a.maxdim : len;
+    int mindim = a.mindim > 1 ? a.mindim : 1;
+    if (len > 1) {
+      while (n > maxdim) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      double scale = 0.0;
+      for (int i = 0; i < len; ++i) scale += __ldcg(a.sig2 + i);
+      if (scale == 0.0) scale = 1.0;
+      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      err /= scale;
+    }
+    if (n < 1) n = 1;
+    a.info[0] = n;
+    a.info[1] = sweeps;
+    a.info[2] = converged;
+    a.info[3] = q;
+    a.derr[0] = err;
+  }
+}
+
+template <int NC>
+void launch_jq_pair(Ctx* ctx, JqArgs& a, int grid) {
+  void* args[] = {&a};
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_pair_kernel<NC>, dim3(grid), dim3(128), args, 0, ctx->stream));
+  ctx->launches++;
+}
+
 // Wn[i][:] = carried (Q^T) part of row perm[i]; rows beyond the numerical rank are zero
 __global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
                                    const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
@@ -705,7 +883,14 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
   if (grid < 1) grid = 1;
-  if (ldy <= 128) launch_jq<2>(ctx, a, grid);
+  static const bool one_warp = getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "onewarp";
+  const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
+  if (!one_warp && half <= 512) {
+    if (half <= 64) launch_jq_pair<1>(ctx, a, grid);
+    else if (half <= 128) launch_jq_pair<2>(ctx, a, grid);
+    else if (half <= 256) launch_jq_pair<4>(ctx, a, grid);
+    else launch_jq_pair<8>(ctx, a, grid);
+  } else if (ldy <= 128) launch_jq<2>(ctx, a, grid);
   else if (ldy <= 256) launch_jq<4>(ctx, a, grid);
   else if (ldy <= 512) launch_jq<8>(ctx, a, grid);
   else if (ldy <= 1024) launch_jq<16>(ctx, a, grid);
