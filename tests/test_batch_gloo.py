@@ -62,3 +62,14 @@ def test_batch_solve_single_process():
     table, results = q.batch_solve(4, lambda i: (i * i, (float(i), 2.0)))
     assert table.shape == (4, 2) and list(table[:, 0]) == [0.0, 1.0, 2.0, 3.0]
     assert results == {0: 0, 1: 1, 2: 4, 3: 9}
+
+
+def test_batch_solve_streams_threads():
+    import itensorqtt_jl_b200 as q
+    seen = []
+    def solve_one(i, slot):
+        seen.append((i, slot))
+        return i, (float(i), float(slot))
+    table, results = q.batch_solve(7, solve_one, streams=3)
+    assert list(table[:, 0]) == [float(i) for i in range(7)]
+    assert sorted(i for i, _ in seen) == list(range(7)) and all(slot == i % 3 for i, slot in seen)
