@@ -1,0 +1,128 @@
+"""GPU edge cases and full-size (BASELINE config) property tests through the C ABI: shortest chains, ragged bond
+dimensions, maxdim = 1, zero right-hand side, rank-deficient two-site tensors, argument errors, and size-independent
+properties at chi = 256 / 512 (isometry, reconstruction, linearity, Krylov orthogonality)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_two_site_chain_matches_dense_solve(lib):
+    n = 2
+    A = O.airy_mpo(n, 1.0, 2.0)
+    b = O.boundary_value_mps(n, 0.7, -0.4)
+    x0 = O.random_mps(n, 2, 3)
+    x = lib.linsolve(A, b, x0, nsweeps=2, maxdim=4, cutoff=0.0, tol=1e-13, krylovdim=4, maxiter=4)
+    xd = np.linalg.solve(O.mpo_to_mat(A), O.mps_to_discrete_function(b))
+    assert rel(O.mps_to_discrete_function(x), xd) < 1e-10
+
+
+def test_ragged_bond_dimensions(lib):
+    """x0 with irregular link dimensions (1,2,3,5,4,2,1): every edge-predicated copy path of the GEMM / matvec kernels."""
+    n = 6
+    rng = np.random.default_rng(5)
+    dims = [1, 2, 3, 5, 4, 2, 1]
+    x0 = [rng.standard_normal((dims[j], 2, dims[j + 1])) for j in range(n)]
+    A = O.airy_mpo(n, 1.0, 3.0)
+    b = O.boundary_value_mps(n, 0.3, 0.2)
+    kw = dict(nsweeps=3, maxdim=8, cutoff=1e-13, tol=1e-12, krylovdim=30, maxiter=10)
+    xo, _ = O.linsolve(A, b, x0, **kw)
+    xg = lib.linsolve(A, b, x0, **kw)
+    assert O.fidelity_defect(xo, xg) <= 1e-10
+    assert O.linkdims(xg) == O.linkdims(xo)
+
+
+def test_maxdim_one_product_state(lib):
+    n = 6
+    A = O.airy_mpo(n, 1.0, 3.0)
+    b = O.boundary_value_mps(n, 0.3, 0.2)
+    x0 = O.random_mps(n, 3, 9)
+    kw = dict(nsweeps=2, maxdim=1, cutoff=0.0, tol=1e-12, krylovdim=16, maxiter=4)
+    xo, _ = O.linsolve(A, b, x0, **kw)
+    xg = lib.linsolve(A, b, x0, **kw)
+    assert O.linkdims(xg) == [1] * (n - 1)
+    assert O.fidelity_defect(xo, xg) <= 1e-9
+
+
+def test_zero_rhs_gives_zero_solution(lib):
+    n = 5
+    A = O.airy_mpo(n, 1.0, 3.0)
+    b = [np.zeros_like(c) for c in O.boundary_value_mps(n, 0.3, 0.2)]
+    x0 = O.random_mps(n, 3, 1)
+    x = lib.linsolve(A, b, x0, nsweeps=1, maxdim=4, cutoff=0.0, tol=1e-12, krylovdim=16, maxiter=4)
+    v = O.mps_to_discrete_function(x)
+    assert np.all(np.isfinite(v)) and np.abs(v).max() < 1e-9
+
+
+def test_split_rank_deficient_and_zero(lib):
+    """Numerically rank-2 two-site tensor (what the first benchmark sweep produces) and the zero tensor."""
+    rng = np.random.default_rng(2)
+    a = c = 32
+    u = rng.standard_normal((2 * a, 2)); v = rng.standard_normal((2, 2 * c))
+    phi = (u @ v).reshape(a, 2, 2, c)
+    for ortho in ("left", "right"):
+        r = lib.split2(phi, ortho=ortho, cutoff=1e-14)
+        assert r["rank"] == 2
+        rec = np.einsum("ask,ktc->astc", r["A"], r["B"])
+        assert rel(rec, phi) < 1e-13
+        r = lib.split2(phi, ortho=ortho, cutoff=0.0, mindim=8, maxdim=8)   # forced bond dimension: padding directions
+        assert r["rank"] == 8
+        rec = np.einsum("ask,ktc->astc", r["A"], r["B"])
+        assert rel(rec, phi) < 1e-13
+        iso = r["A"].reshape(2 * a, -1) if ortho == "left" else r["B"].reshape(-1, 2 * c).T
+        G = iso.T @ iso
+        assert np.abs(G - np.diag(np.diag(G))).max() < 1e-12 and np.all((np.abs(np.diag(G) - 1) < 1e-12) | (np.abs(np.diag(G)) < 1e-12))
+    z = lib.split2(np.zeros((4, 2, 2, 4)), ortho="left", cutoff=0.0)
+    assert z["rank"] >= 1 and np.all(np.isfinite(z["A"])) and np.all(np.isfinite(z["B"]))
+
+
+def test_argument_errors_are_reported(lib):
+    n = 4
+    A = O.airy_mpo(n, 1.0, 3.0)
+    b = O.boundary_value_mps(n, 0.3, 0.2)
+    x0 = O.random_mps(n + 1, 2, 1)
+    with pytest.raises(lib.QttError):
+        lib.linsolve(A, b, x0, nsweeps=1, maxdim=4, cutoff=0.0)          # chain length mismatch
+    with pytest.raises(lib.QttError):
+        lib.linsolve(A, b, O.random_mps(n, 2, 1), nsweeps=1, maxdim=4, cutoff=0.0, krylovdim=1000)   # krylovdim out of range
+    with pytest.raises(ValueError):
+        lib.DeviceMPS([np.zeros((1, 3, 1))])                              # site dimension must be 2
+
+
+@pytest.mark.parametrize("chi,w", [(256, 4), (256, 5), (512, 3), (200, 3), (129, 3)])
+def test_matvec_full_size_properties(lib, chi, w):
+    """Linearity, and agreement with the oracle on one random probe direction <u, P v> (cheap at full size)."""
+    rng = np.random.default_rng(chi + w)
+    L = rng.standard_normal((chi, w, chi)); R = rng.standard_normal((chi, w, chi))
+    W1 = rng.standard_normal((w, w, 2, 2)); W2 = rng.standard_normal((w, w, 2, 2))
+    v1 = rng.standard_normal((chi, 2, 2, chi)); v2 = rng.standard_normal((chi, 2, 2, chi))
+    o1, _ = lib.matvec2(L, W1, W2, R, v1)
+    o2, _ = lib.matvec2(L, W1, W2, R, v2)
+    o12, _ = lib.matvec2(L, W1, W2, R, 0.25 * v1 + 3.0 * v2)
+    assert rel(o12, 0.25 * o1 + 3.0 * o2) < 1e-13
+    assert rel(o1, O.matvec2(L, W1, W2, R, v1)) < 1e-13
+
+
+def test_split_headline_isometry_chi256(lib):
+    """512 x 512 graded two-site tensor, maxdim = 256: kept factor is an isometry, discarded weight matches LAPACK."""
+    rng = np.random.default_rng(7)
+    a = c = 256
+    U = np.linalg.qr(rng.standard_normal((2 * a, 2 * a)))[0]; V = np.linalg.qr(rng.standard_normal((2 * c, 2 * c)))[0]
+    s = 10.0 ** (-np.arange(2 * a) * 0.05)
+    phi = ((U * s) @ V.T).reshape(a, 2, 2, c)
+    for ortho in ("left", "right"):
+        r = lib.split2(phi, ortho=ortho, cutoff=3e-20, maxdim=256)
+        k = r["rank"]
+        _, S, _, err = O.svd_truncated(phi.reshape(2 * a, 2 * c), cutoff=3e-20, maxdim=256)
+        assert k == len(S)
+        iso = r["A"].reshape(2 * a, k) if ortho == "left" else r["B"].reshape(k, 2 * c).T
+        assert np.abs(iso.T @ iso - np.eye(k)).max() < 1e-12
+        rec = np.einsum("ask,ktc->astc", r["A"], r["B"]).reshape(2 * a, 2 * c)
+        assert abs(np.linalg.norm(rec - phi.reshape(2 * a, 2 * c)) ** 2 / np.linalg.norm(phi) ** 2 - err) < 1e-6 * err + 1e-28
+        assert np.abs(r["sigma"][:k] - S).max() < 1e-13 * S[0]
