@@ -208,11 +208,10 @@ __device__ __forceinline__ unsigned ld_acq_u32(const unsigned* p) {
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // one cumulative release-RED instead of membar + atomic (svd_qr.cu:grid_sync)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
     while ((int)(ld_acq_u32(counter) - target) < 0) {
     }
-    __threadfence();
   }
   __syncthreads();
 }

@@ -30,11 +30,9 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
     while (ld_acquire(counter) < target) {
     }
-    __threadfence();
   }
   __syncthreads();
 }

@@ -378,15 +378,16 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 
+// Grid barrier on a monotonic counter (cooperative launch guarantees co-residency).  Arrival is ONE release-RED: the
+// release is cumulative over the CTA's stores ordered before it by bar.sync, so no separate membar round trip is paid;
+// the waiters poll with acquire loads.
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
     while (ld_acquire(counter) < target) {
     }
-    __threadfence();
   }
   __syncthreads();
 }
