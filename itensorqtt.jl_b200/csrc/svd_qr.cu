@@ -767,6 +767,249 @@ void launch_jq_pair(Ctx* ctx, JqArgs& a, int grid) {
   ctx->launches++;
 }
 
+// ---- block-cyclic variant: 4-row blocks, several rotation steps per grid barrier ---------------------------------------
+// A round of the row-cyclic kernels costs ~3 us and is pure latency (barrier + L2 round trips), whatever the number of
+// rows.  Here the tournament is played between BLOCKS of 4 rows: a CTA (4 warp pairs) takes two blocks P and M, keeps
+// the P rows in registers and rotates them against all four M rows in 4 steps, the M rows circulating between the
+// warp pairs through shared memory (one __syncthreads per step, ~0.4 us).  One grid barrier therefore covers 4
+// rotation steps; the pairs inside a block are swept by three extra global rounds per sweep.  It is still a cyclic
+// one-sided Jacobi ordering (every row pair exactly once per sweep).
+constexpr int JB = 4;
+
+struct RotState {
+  bool rotated;
+};
+
+// rows held as half-rows in registers (za: row A, zb: row B); role 0 computes the angle from the R part
+template <int NC>
+__device__ __forceinline__ bool rotate_halfrows(double2 (&za)[NC], double2 (&zb)[NC], int role, int unit_in_cta, double (*cs_s)[4], double tol,
+                                                double thr, int lane) {
+  if (role == 0) {
+    double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      alpha += za[k].x * za[k].x + za[k].y * za[k].y;
+      beta += zb[k].x * zb[k].x + zb[k].y * zb[k].y;
+      gamma += za[k].x * zb[k].x + za[k].y * zb[k].y;
+    }
+    alpha = warp_sum(alpha);
+    beta = warp_sum(beta);
+    gamma = warp_sum(gamma);
+    double c = 1.0, s = 0.0, rot = 0.0;
+    if ((alpha > thr) && (beta > thr)) {
+      const double lim = sqrt(alpha) * sqrt(beta);
+      if ((lim > 0.0) && (fabs(gamma) > tol * lim)) {
+        jrotation(alpha, beta, gamma, c, s);
+        rot = 1.0;
+      }
+    }
+    if (lane == 0) {
+      cs_s[unit_in_cta][0] = c;
+      cs_s[unit_in_cta][1] = s;
+      cs_s[unit_in_cta][2] = rot;
+    }
+  }
+  pair_bar(1 + unit_in_cta);
+  const double c = cs_s[unit_in_cta][0], s = cs_s[unit_in_cta][1];
+  const bool rot = cs_s[unit_in_cta][2] != 0.0;
+  if (rot) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const double2 x = za[k], y = zb[k];
+      za[k] = make_double2(c * x.x - s * y.x, c * x.y - s * y.y);
+      zb[k] = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
+    }
+  }
+  pair_bar(1 + unit_in_cta);  // cs_s may be rewritten by the next rotation of this unit
+  return rot;
+}
+
+template <int NC>
+__device__ __forceinline__ void load_half(double2 (&z)[NC], const double* row, int len, int lane, bool live) {
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int col = 2 * lane + 64 * k;
+    z[k] = (live && col < len) ? __ldcg(reinterpret_cast<const double2*>(row + col)) : make_double2(0.0, 0.0);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void store_half(const double2 (&z)[NC], double* row, int len, int lane, bool live) {
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int col = 2 * lane + 64 * k;
+    if (live && col < len) __stcg(reinterpret_cast<double2*>(row + col), z[k]);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
+  extern __shared__ double mbuf[];  // [2][JB][ld]: circulating M rows
+  __shared__ double cs_s[4][4];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int unit = warp >> 1;   // 0..3
+  const int role = warp & 1;    // 0: R part (angles), 1: carried part
+  const int q = a.ctl->r;
+  const double thr = a.ctl->thr;
+  const int nbk = (((q + JB - 1) / JB) + 1) & ~1;  // blocks, padded to even
+  const int nslots = nbk / 2, orounds = nbk - 1;
+  const int c_lo = role == 0 ? 0 : a.ndot;
+  const int len = role == 0 ? a.ndot : a.ld - a.ndot;
+  const int ld = a.ld;
+  unsigned target = 0;
+  int sweeps = 0;
+  int converged = (q < 2) ? 1 : 0;
+  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
+    bool rotated = false;
+    // ---- pairs inside a block: three rounds over all blocks, rows through global memory
+    for (int st = 0; st < 3; ++st) {
+      const int gunit = blockIdx.x * 4 + unit, gunits = gridDim.x * 4;
+      for (int pidx = gunit; pidx < 2 * nbk; pidx += gunits) {
+        const int blk = pidx >> 1, half = pidx & 1;
+        int u0, u1;
+        if (st == 0) { u0 = half ? 2 : 0; u1 = half ? 3 : 1; }
+        else if (st == 1) { u0 = half ? 1 : 0; u1 = half ? 3 : 2; }
+        else { u0 = half ? 1 : 0; u1 = half ? 2 : 3; }
+        const int ia = blk * JB + u0, ib = blk * JB + u1;
+        const bool live = ia < q && ib < q;
+        double2 za[NC], zb[NC];
+        double* ra = a.Y + (size_t)ia * ld + c_lo;
+        double* rb = a.Y + (size_t)ib * ld + c_lo;
+        load_half<NC>(za, ra, len, lane, live);
+        load_half<NC>(zb, rb, len, lane, live);
+        if (rotate_halfrows<NC>(za, zb, role, unit, cs_s, a.tol, thr, lane)) {
+          rotated = true;
+          store_half<NC>(za, ra, len, lane, live);
+          store_half<NC>(zb, rb, len, lane, live);
+        }
+      }
+      grid_sync(a.sync, target);
+    }
+    // ---- block tournament
+    for (int R = 0; R < orounds; ++R) {
+      for (int i = blockIdx.x; i < nslots; i += gridDim.x) {
+        int bp, bm;
+        if (i == 0) {
+          bp = R;
+          bm = nbk - 1;
+        } else {
+          bp = (R + i) % (nbk - 1);
+          bm = (R - i + (nbk - 1)) % (nbk - 1);
+        }
+        const int ip = bp * JB + unit;
+        const bool plive = ip < q;
+        double2 zp[NC], zm[NC];
+        double* rp = a.Y + (size_t)ip * ld + c_lo;
+        load_half<NC>(zp, rp, len, lane, plive);
+        int v = unit;  // M row currently held
+        load_half<NC>(zm, a.Y + (size_t)(bm * JB + v) * ld + c_lo, len, lane, bm * JB + v < q);
+        bool pdirty = false;
+#pragma unroll 1
+        for (int t = 0; t < JB; ++t) {
+          const bool rot = rotate_halfrows<NC>(zp, zm, role, unit, cs_s, a.tol, thr, lane);
+          pdirty |= rot;
+          rotated |= rot;
+          if (t + 1 < JB) {
+            // hand M[v] to the previous unit, take M[v + 1] from the next one
+            double* wb = mbuf + ((size_t)(t & 1) * JB + v) * ld + c_lo;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              const int col = 2 * lane + 64 * k;
+              if (col < len) *reinterpret_cast<double2*>(wb + col) = zm[k];
+            }
+            __syncthreads();
+            v = (v + 1) & (JB - 1);
+            const double* rbuf = mbuf + ((size_t)(t & 1) * JB + v) * ld + c_lo;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              const int col = 2 * lane + 64 * k;
+              zm[k] = col < len ? *reinterpret_cast<const double2*>(rbuf + col) : make_double2(0.0, 0.0);
+            }
+          }
+        }
+        if (pdirty) store_half<NC>(zp, rp, len, lane, plive);
+        // the M row may have been rotated by another unit: always written back
+        store_half<NC>(zm, a.Y + (size_t)(bm * JB + v) * ld + c_lo, len, lane, bm * JB + v < q);
+        if (nslots > (int)gridDim.x) __syncthreads();  // mbuf is reused by this CTA's next slot
+      }
+      grid_sync(a.sync, target);
+    }
+    if (rotated && lane == 0 && role == 0) atomicAdd(a.sync + 2 + sw, 1u);
+    grid_sync(a.sync, target);
+    sweeps = sw + 1;
+    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
+  }
+  const int gw = blockIdx.x * 8 + warp;
+  const int GW = gridDim.x * 8;
+  for (int i = gw; i < q; i += GW) {
+    const double* ri = a.Y + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ndot; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (!(acc > thr)) acc = 0.0;
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
+    if (i < q) {
+      const double ni = __ldcg(a.norms + i);
+      int rank = 0;
+      for (int j = 0; j < q; ++j) {
+        const double nj = __ldcg(a.norms + j);
+        rank += (nj > ni) || (nj == ni && j < i);
+      }
+      a.perm[rank] = i;
+      a.sig2[rank] = ni;
+    } else {
+      a.perm[i] = -1;
+      a.sig2[i] = 0.0;
+    }
+  }
+  grid_sync(a.sync, target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int lenp = a.kmax;
+    int n = lenp;
+    double err = 0.0;
+    int maxdim = a.maxdim < lenp ? a.maxdim : lenp;
+    int mindim = a.mindim > 1 ? a.mindim : 1;
+    if (lenp > 1) {
+      while (n > maxdim) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      double scale = 0.0;
+      for (int i = 0; i < lenp; ++i) scale += __ldcg(a.sig2 + i);
+      if (scale == 0.0) scale = 1.0;
+      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
+        err += __ldcg(a.sig2 + n - 1);
+        --n;
+      }
+      err /= scale;
+    }
+    if (n < 1) n = 1;
+    a.info[0] = n;
+    a.info[1] = sweeps;
+    a.info[2] = converged;
+    a.info[3] = q;
+    a.derr[0] = err;
+  }
+}
+
+template <int NC>
+void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
+  static bool configured = false;
+  if (!configured) {
+    QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  void* args[] = {&a};
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC>, dim3(grid), dim3(256), args, smem, ctx->stream));
+  ctx->launches++;
+}
+
 // Wn[i][:] = carried (Q^T) part of row perm[i]; rows beyond the numerical rank are zero
 __global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
                                    const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
@@ -886,7 +1129,18 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   if (grid < 1) grid = 1;
   static const bool one_warp = getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "onewarp";
   const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
-  if (!one_warp && half <= 512) {
+  static const bool blocked = !(getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "pair");
+  if (!one_warp && blocked && half <= 512 && kmax >= 16) {
+    // block-cyclic kernel: one CTA per pair of 4-row blocks
+    const int nbk = (((kmax + JB - 1) / JB) + 1) & ~1;
+    int bgrid = nbk / 2;
+    if (bgrid > ctx->sms) bgrid = ctx->sms;
+    const size_t smem = (size_t)2 * JB * ldy * sizeof(double);
+    if (half <= 64) launch_jq_block<1>(ctx, a, bgrid, smem);
+    else if (half <= 128) launch_jq_block<2>(ctx, a, bgrid, smem);
+    else if (half <= 256) launch_jq_block<4>(ctx, a, bgrid, smem);
+    else launch_jq_block<8>(ctx, a, bgrid, smem);
+  } else if (!one_warp && half <= 512) {
     if (half <= 64) launch_jq_pair<1>(ctx, a, grid);
     else if (half <= 128) launch_jq_pair<2>(ctx, a, grid);
     else if (half <= 256) launch_jq_pair<4>(ctx, a, grid);
