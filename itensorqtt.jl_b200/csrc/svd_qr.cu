@@ -774,16 +774,14 @@ void launch_jq_pair(Ctx* ctx, JqArgs& a, int grid) {
 // warp pairs through shared memory (one __syncthreads per step, ~0.4 us).  One grid barrier therefore covers 4
 // rotation steps; the pairs inside a block are swept by three extra global rounds per sweep.  It is still a cyclic
 // one-sided Jacobi ordering (every row pair exactly once per sweep).
-constexpr int JB = 4;
 
-struct RotState {
-  bool rotated;
-};
 
 // rows held as half-rows in registers (za: row A, zb: row B); role 0 computes the angle from the R part
 template <int NC>
-__device__ __forceinline__ bool rotate_halfrows(double2 (&za)[NC], double2 (&zb)[NC], int role, int unit_in_cta, double (*cs_s)[4], double tol,
-                                                double thr, int lane) {
+__device__ __forceinline__ bool rotate_halfrows(double2 (&za)[NC], double2 (&zb)[NC], int role, int unit_in_cta, double (*cs_s)[8], int& parity,
+                                                double tol, double thr, int lane) {
+  double* slot = cs_s[unit_in_cta] + 4 * parity;  // double-buffered by call parity: one pair barrier per rotation
+  parity ^= 1;
   if (role == 0) {
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
@@ -796,22 +794,20 @@ __device__ __forceinline__ bool rotate_halfrows(double2 (&za)[NC], double2 (&zb)
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
     double c = 1.0, s = 0.0, rot = 0.0;
-    if ((alpha > thr) && (beta > thr)) {
-      const double lim = sqrt(alpha) * sqrt(beta);
-      if ((lim > 0.0) && (fabs(gamma) > tol * lim)) {
-        jrotation(alpha, beta, gamma, c, s);
-        rot = 1.0;
-      }
+    // |gamma| > tol sqrt(alpha beta), without the square roots
+    if ((alpha > thr) && (beta > thr) && (gamma * gamma > (tol * tol) * (alpha * beta))) {
+      jrotation(alpha, beta, gamma, c, s);
+      rot = 1.0;
     }
     if (lane == 0) {
-      cs_s[unit_in_cta][0] = c;
-      cs_s[unit_in_cta][1] = s;
-      cs_s[unit_in_cta][2] = rot;
+      slot[0] = c;
+      slot[1] = s;
+      slot[2] = rot;
     }
   }
   pair_bar(1 + unit_in_cta);
-  const double c = cs_s[unit_in_cta][0], s = cs_s[unit_in_cta][1];
-  const bool rot = cs_s[unit_in_cta][2] != 0.0;
+  const double c = slot[0], s = slot[1];
+  const bool rot = slot[2] != 0.0;
   if (rot) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
@@ -820,7 +816,6 @@ __device__ __forceinline__ bool rotate_halfrows(double2 (&za)[NC], double2 (&zb)
       zb[k] = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
     }
   }
-  pair_bar(1 + unit_in_cta);  // cs_s may be rewritten by the next rotation of this unit
   return rot;
 }
 
@@ -841,13 +836,14 @@ __device__ __forceinline__ void store_half(const double2 (&z)[NC], double* row, 
   }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
+template <int NC, int JB>
+__global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
   extern __shared__ double mbuf[];  // [2][JB][ld]: circulating M rows
-  __shared__ double cs_s[4][4];
+  __shared__ double cs_s[JB][8];
+  int parity = 0;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int unit = warp >> 1;   // 0..3
+  const int unit = warp >> 1;   // 0..JB-1
   const int role = warp & 1;    // 0: R part (angles), 1: carried part
   const int q = a.ctl->r;
   const double thr = a.ctl->thr;
@@ -862,14 +858,13 @@ __global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
   for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
     bool rotated = false;
     // ---- pairs inside a block: three rounds over all blocks, rows through global memory
-    for (int st = 0; st < 3; ++st) {
-      const int gunit = blockIdx.x * 4 + unit, gunits = gridDim.x * 4;
-      for (int pidx = gunit; pidx < 2 * nbk; pidx += gunits) {
-        const int blk = pidx >> 1, half = pidx & 1;
-        int u0, u1;
-        if (st == 0) { u0 = half ? 2 : 0; u1 = half ? 3 : 1; }
-        else if (st == 1) { u0 = half ? 1 : 0; u1 = half ? 3 : 2; }
-        else { u0 = half ? 1 : 0; u1 = half ? 2 : 3; }
+    for (int st = 0; st < JB - 1; ++st) {
+      const int gunit = blockIdx.x * JB + unit, gunits = gridDim.x * JB;
+      for (int pidx = gunit; pidx < (JB / 2) * nbk; pidx += gunits) {
+        const int blk = pidx / (JB / 2), i = pidx % (JB / 2);
+        int u0, u1;  // round-robin tournament inside the block
+        if (i == 0) { u0 = st; u1 = JB - 1; }
+        else { u0 = (st + i) % (JB - 1); u1 = (st - i + (JB - 1)) % (JB - 1); }
         const int ia = blk * JB + u0, ib = blk * JB + u1;
         const bool live = ia < q && ib < q;
         double2 za[NC], zb[NC];
@@ -877,7 +872,7 @@ __global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
         double* rb = a.Y + (size_t)ib * ld + c_lo;
         load_half<NC>(za, ra, len, lane, live);
         load_half<NC>(zb, rb, len, lane, live);
-        if (rotate_halfrows<NC>(za, zb, role, unit, cs_s, a.tol, thr, lane)) {
+        if (rotate_halfrows<NC>(za, zb, role, unit, cs_s, parity, a.tol, thr, lane)) {
           rotated = true;
           store_half<NC>(za, ra, len, lane, live);
           store_half<NC>(zb, rb, len, lane, live);
@@ -906,7 +901,7 @@ __global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
         bool pdirty = false;
 #pragma unroll 1
         for (int t = 0; t < JB; ++t) {
-          const bool rot = rotate_halfrows<NC>(zp, zm, role, unit, cs_s, a.tol, thr, lane);
+          const bool rot = rotate_halfrows<NC>(zp, zm, role, unit, cs_s, parity, a.tol, thr, lane);
           pdirty |= rot;
           rotated |= rot;
           if (t + 1 < JB) {
@@ -939,8 +934,8 @@ __global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
     sweeps = sw + 1;
     if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
   }
-  const int gw = blockIdx.x * 8 + warp;
-  const int GW = gridDim.x * 8;
+  const int gw = blockIdx.x * (2 * JB) + warp;
+  const int GW = gridDim.x * (2 * JB);
   for (int i = gw; i < q; i += GW) {
     const double* ri = a.Y + (size_t)i * a.ld;
     double acc = 0.0;
@@ -998,15 +993,15 @@ __global__ void __launch_bounds__(256) jacobi_qr_block_kernel(JqArgs a) {
   }
 }
 
-template <int NC>
+template <int NC, int JB>
 void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
   static bool configured = false;
   if (!configured) {
-    QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   void* args[] = {&a};
-  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC>, dim3(grid), dim3(256), args, smem, ctx->stream));
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC, JB>, dim3(grid), dim3(64 * JB), args, smem, ctx->stream));
   ctx->launches++;
 }
 
@@ -1131,15 +1126,27 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
   static const bool blocked = !(getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "pair");
   if (!one_warp && blocked && half <= 512 && kmax >= 16) {
-    // block-cyclic kernel: one CTA per pair of 4-row blocks
-    const int nbk = (((kmax + JB - 1) / JB) + 1) & ~1;
+    // block-cyclic kernel: one CTA per pair of JB-row blocks
+    static const int jb = getenv("QTT_JB") ? atoi(getenv("QTT_JB")) : 4;
+    const int nbk = (((kmax + jb - 1) / jb) + 1) & ~1;
     int bgrid = nbk / 2;
     if (bgrid > ctx->sms) bgrid = ctx->sms;
-    const size_t smem = (size_t)2 * JB * ldy * sizeof(double);
-    if (half <= 64) launch_jq_block<1>(ctx, a, bgrid, smem);
-    else if (half <= 128) launch_jq_block<2>(ctx, a, bgrid, smem);
-    else if (half <= 256) launch_jq_block<4>(ctx, a, bgrid, smem);
-    else launch_jq_block<8>(ctx, a, bgrid, smem);
+    const size_t smem = (size_t)2 * jb * ldy * sizeof(double);
+    if (jb == 8 && smem <= 200 * 1024) {
+      if (half <= 64) launch_jq_block<1, 8>(ctx, a, bgrid, smem);
+      else if (half <= 128) launch_jq_block<2, 8>(ctx, a, bgrid, smem);
+      else if (half <= 256) launch_jq_block<4, 8>(ctx, a, bgrid, smem);
+      else launch_jq_block<8, 8>(ctx, a, bgrid, smem);
+    } else {
+      const int nb4 = (((kmax + 3) / 4) + 1) & ~1;
+      int g4 = nb4 / 2;
+      if (g4 > ctx->sms) g4 = ctx->sms;
+      const size_t smem4 = (size_t)2 * 4 * ldy * sizeof(double);
+      if (half <= 64) launch_jq_block<1, 4>(ctx, a, g4, smem4);
+      else if (half <= 128) launch_jq_block<2, 4>(ctx, a, g4, smem4);
+      else if (half <= 256) launch_jq_block<4, 4>(ctx, a, g4, smem4);
+      else launch_jq_block<8, 4>(ctx, a, g4, smem4);
+    }
   } else if (!one_warp && half <= 512) {
     if (half <= 64) launch_jq_pair<1>(ctx, a, grid);
     else if (half <= 128) launch_jq_pair<2>(ctx, a, grid);
