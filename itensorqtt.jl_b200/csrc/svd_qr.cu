@@ -407,13 +407,16 @@ struct JqArgs {
   double cutoff;
   int maxdim, mindim;
   const QrCtl* ctl;
+  long long* dbg;  // optional (QTT_TRACE): cycle counters of CTA 0 [barrier, load, steps, store]
 };
 
+// Jacobi rotation that orthogonalises two rows with |a|^2 = alpha, |b|^2 = beta, a.b = gamma: tan(theta) = t is the
+// smaller root of t^2 + 2 zeta t - 1 = 0, zeta = (beta - alpha) / (2 gamma), written with ONE division and one
+// (overflow-safe) hypot: t = 2 gamma / (d + sign(d) hypot(d, 2 gamma)), d = beta - alpha.
 __device__ __forceinline__ void jrotation(double alpha, double beta, double gamma, double& c, double& s) {
-  double zeta = (beta - alpha) / (2.0 * gamma);
-  double t;
-  if (fabs(zeta) > 1e150) t = 0.5 / zeta;
-  else t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double d = beta - alpha, g2 = 2.0 * gamma;
+  const double h = hypot(d, g2);
+  const double t = g2 / (d + copysign(h, d));
   c = rsqrt(1.0 + t * t);
   s = c * t;
 }
@@ -882,6 +885,7 @@ __global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
     }
     // ---- block tournament
     for (int R = 0; R < orounds; ++R) {
+      long long tc0 = clock64();
       for (int i = blockIdx.x; i < nslots; i += gridDim.x) {
         int bp, bm;
         if (i == 0) {
@@ -899,6 +903,8 @@ __global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
         int v = unit;  // M row currently held
         load_half<NC>(zm, a.Y + (size_t)(bm * JB + v) * ld + c_lo, len, lane, bm * JB + v < q);
         bool pdirty = false;
+        long long tc1 = clock64();
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[1] += tc1 - tc0;
 #pragma unroll 1
         for (int t = 0; t < JB; ++t) {
           const bool rot = rotate_halfrows<NC>(zp, zm, role, unit, cs_s, parity, a.tol, thr, lane);
@@ -922,12 +928,18 @@ __global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
             }
           }
         }
+        long long tc2 = clock64();
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[2] += tc2 - tc1;
         if (pdirty) store_half<NC>(zp, rp, len, lane, plive);
         // the M row may have been rotated by another unit: always written back
         store_half<NC>(zm, a.Y + (size_t)(bm * JB + v) * ld + c_lo, len, lane, bm * JB + v < q);
         if (nslots > (int)gridDim.x) __syncthreads();  // mbuf is reused by this CTA's next slot
+        tc0 = clock64();
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] += tc0 - tc2;
       }
+      long long tb0 = clock64();
       grid_sync(a.sync, target);
+      if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { a.dbg[0] += clock64() - tb0; a.dbg[4] += 1; }
     }
     if (rotated && lane == 0 && role == 0) atomicAdd(a.sync + 2 + sw, 1u);
     grid_sync(a.sync, target);
@@ -1118,6 +1130,11 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   if (a.maxdim > kmax) a.maxdim = kmax;
   a.mindim = mindim;
   a.ctl = ctl;
+  a.dbg = nullptr;
+  if (ctx->profiling && getenv("QTT_TRACE") != nullptr) {
+    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(8));
+    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 64, ctx->stream));
+  }
   const int npairs = ((kmax + 1) & ~1) / 2;
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
@@ -1172,6 +1189,13 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evq, evj);
     fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: numerical rank %d, jacobi %d sweeps %.3f ms (after QR)\n", q, p, h_info[3], h_info[1], ms);
+    if (a.dbg) {
+      long long h[8];
+      cudaMemcpy(h, a.dbg, 64, cudaMemcpyDeviceToHost);
+      if (h[4] > 0)
+        fprintf(stderr, "[qtt trace]   block jacobi CTA0 cycles per outer round: barrier %.0f load %.0f steps %.0f store %.0f (%lld rounds)\n",
+                (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
+    }
     cudaEventDestroy(evq);
     cudaEventDestroy(evj);
   }
