@@ -175,6 +175,10 @@ void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double
 bool kry_cgs2_fused_ok(const Ctx* ctx, size_t len);
 void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, double* vnext, double* S, int off_h1, int off_h2,
                     int off_nres2, int off_done, int post, double a0, double a1, double tol, volatile double* hstat);
+// single-CTA local GMRES for small bonds (krylov_small.cu)
+bool gmres_small_ok(int chil, int chir, int wl, int wr, int kd);
+void gmres_small(Ctx* ctx, const double* L, const double* W12, const double* R, const double* beff, double* x, int chil, int chir, int wl,
+                 int wr, double a0, double a1, double tol, int kd, int maxiter, bool fixed, double* V, double* stats_dev);
 void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out /* device scalar */);
 void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out,
                   const double* done_dev = nullptr);

@@ -71,6 +71,35 @@ __device__ inline void gmres_step_scalars(double* S, int k, double a0, double a1
   }
 }
 
+// Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
+// k >= 0: use k columns.  k < 0: use the device-side step count S_K and zero-fill yk up to kd = -k.
+__device__ inline void gmres_solve_scalars(double* S, int k_or_neg_kd, int ld) {
+  int k = k_or_neg_kd;
+  int kd = 0;
+  if (k < 0) { kd = -k; k = (int)S[S_K]; }
+  double* Rm = S + OFF_R;
+  double* y = S + OFF_Y;
+  double* gc = S + OFF_GC;
+  double* gs = S + OFF_GS;
+  double* yk = S + OFF_YK;
+  double* coef = S + OFF_COEF;
+  for (int i = k - 1; i >= 0; --i) {
+    double acc = y[i];
+    for (int j = i + 1; j < k; ++j) acc -= Rm[i * ld + j] * yk[j];
+    yk[i] = acc / Rm[i * ld + i];
+  }
+  for (int i = 0; i <= k; ++i) coef[i] = 0.0;
+  coef[k] = 1.0;
+  for (int i = k - 1; i >= 0; --i) {
+    double t1 = coef[i], t2 = coef[i + 1];
+    coef[i] = gc[i] * t1 - gs[i] * t2;
+    coef[i + 1] = gs[i] * t1 + gc[i] * t2;
+  }
+  for (int i = 0; i <= k; ++i) coef[i] *= y[k];
+  S[S_R0N2] = y[k] * y[k];
+  for (int i = k; i < kd; ++i) yk[i] = 0.0;
+}
+
 // column k-1 of the Lanczos projected matrix from the CGS2 coefficients; subdiagonal = residual norm
 __device__ inline void lanczos_step_scalars(double* S, int k, int ld) {
   if (S[S_DONE] != 0.0) return;

@@ -31,33 +31,7 @@ __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, doub
 }
 
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
-__global__ void gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) {
-  // k >= 0: use k columns.  k < 0: use the device-side step count S_K and zero-fill yk up to kd = -k.
-  int k = k_or_neg_kd;
-  int kd = 0;
-  if (k < 0) { kd = -k; k = (int)S[S_K]; }
-  double* Rm = S + OFF_R;
-  double* y = S + OFF_Y;
-  double* gc = S + OFF_GC;
-  double* gs = S + OFF_GS;
-  double* yk = S + OFF_YK;
-  double* coef = S + OFF_COEF;
-  for (int i = k - 1; i >= 0; --i) {
-    double acc = y[i];
-    for (int j = i + 1; j < k; ++j) acc -= Rm[i * ld + j] * yk[j];
-    yk[i] = acc / Rm[i * ld + i];
-  }
-  for (int i = 0; i <= k; ++i) coef[i] = 0.0;
-  coef[k] = 1.0;
-  for (int i = k - 1; i >= 0; --i) {
-    double t1 = coef[i], t2 = coef[i + 1];
-    coef[i] = gc[i] * t1 - gs[i] * t2;
-    coef[i + 1] = gs[i] * t1 + gc[i] * t2;
-  }
-  for (int i = 0; i <= k; ++i) coef[i] *= y[k];
-  S[S_R0N2] = y[k] * y[k];
-  for (int i = k; i < kd; ++i) yk[i] = 0.0;
-}
+__global__ void gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) { gmres_solve_scalars(S, k_or_neg_kd, ld); }
 
 __global__ void set_scalars_kernel(double* p, int n, double v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,6 +489,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const double* Rp = RA[j + 2].p;
           MatvecFn mv = [&](const double* in, double* out) { matvec2(ctx, Lp, W12, Rp, in, out, chil, chir, wl, wr, mvscr); };
           LocalStats st;
+          bool small_pending = false;
           const double tk0 = info.t_krylov, ts0 = info.t_svd, te0 = info.t_env;
           const int kdl = (size_t)kd < len ? kd : (int)len;  // a Krylov space cannot exceed the local dimension
           {
@@ -523,17 +498,26 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               double* beff = ctx->arena.alloc(len);
               project_rhs(ctx, LB[j].p, b->core[j].p, b->core[j + 1].p, RB[j + 2].p, beff, chil, chir, (int)b->chi[j], (int)b->chi[j + 1],
                           (int)b->chi[j + 2]);
-              gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws, st);
+              if (gmres_small_ok(chil, chir, wl, wr, kdl)) {
+                // whole local solve in one single-CTA kernel (krylov_small.cu); statistics are read after the split's sync
+                gmres_small(ctx, Lp, W12, Rp, beff, phi, chil, chir, wl, wr, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws.V, ctx->d_scal + 8);
+                QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 72, ctx->d_scal + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                small_pending = true;
+              } else {
+                gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws, st);
+              }
             } else {
               lanczos_local(ctx, mv, phi, len, P.target, P.tol, kdl, maxiter, fixed, ws, st);
               info.energy = st.theta;
             }
           }
-          if (fixed && is_lin)
+          if (fixed && is_lin && !small_pending)
             QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 70, ctx->d_scal + S_BETA, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-          info.matvecs += st.matvecs;
-          info.flops_matvec += (double)st.matvecs * matvec_flops(chil, chir, wl, wm, wr);
-          if (st.resid > info.solver_resid) info.solver_resid = st.resid;
+          if (!small_pending) {
+            info.matvecs += st.matvecs;
+            info.flops_matvec += (double)st.matvecs * matvec_flops(chil, chir, wl, wm, wr);
+            if (st.resid > info.solver_resid) info.solver_resid = st.resid;
+          }
           if (P.normalize) {
             kry_nrm2sq(ctx, phi, len, ctx->d_scal + S_TMP);
             long nb = (long)((len + 255) / 256);
@@ -555,7 +539,14 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
             PhaseTimer pt(ctx, &info.t_svd);
             sr = split2(ctx, phi, chil, chir, dir, cutoff, maxdim, mindim, x.core[j].p, x.core[j + 1].p, nullptr, P.svd_max_sweeps);
           }
-          if (fixed && is_lin && ctx->h_scal[70] > info.solver_resid) info.solver_resid = ctx->h_scal[70];  // split2 synchronised
+          if (small_pending) {  // split2 synchronised the stream: the single-CTA solver's statistics have arrived
+            const double mvs = ctx->h_scal[72];
+            info.matvecs += (int64_t)mvs;
+            info.flops_matvec += mvs * matvec_flops(chil, chir, wl, wm, wr);
+            if (ctx->h_scal[73] > info.solver_resid) info.solver_resid = ctx->h_scal[73];
+          } else if (fixed && is_lin && ctx->h_scal[70] > info.solver_resid) {
+            info.solver_resid = ctx->h_scal[70];  // split2 synchronised
+          }
           x.chi[j + 1] = sr.rank;
           if (sr.truncerr > info.maxtruncerr) info.maxtruncerr = sr.truncerr;
           if (sr.sweeps > info.svd_sweeps_max) info.svd_sweeps_max = sr.sweeps;

@@ -90,3 +90,21 @@ def test_dmrg_target_lanczos(lib):
     ev = (v @ Lm @ v) / (v @ v)
     assert abs(ev - target) < 1e-8
     assert abs(info[-1]["energy"] - target) < 1e-8
+
+
+def test_multi_kernel_path_large_bonds(lib):
+    """Bonds with 4 chi_l chi_r > 1024 take the multi-launch solver (fused DMMA matvec + cooperative CGS2 kernel) instead of
+    the single-CTA small-bond kernel: same answer as the oracle in fixed-work mode and in converged mode."""
+    n = 10
+    A, b, Am, bv = _airy(n, 1.0, 3.0)
+    x0 = O.random_mps(n, 24, 5)                       # interior bonds 24: len = 2304
+    kw = dict(nsweeps=1, maxdim=24, cutoff=1e-13, fixed_matvecs=10)
+    xo, _ = O.linsolve(A, b, x0, **kw)
+    xg = lib.linsolve(A, b, x0, **kw)
+    assert O.fidelity_defect(xo, xg) <= 1e-10
+    kw = dict(nsweeps=2, maxdim=24, cutoff=1e-13, tol=1e-11, krylovdim=30, maxiter=6)
+    xo, _ = O.linsolve(A, b, x0, **kw)
+    xg = lib.linsolve(A, b, x0, **kw)
+    assert O.fidelity_defect(xo, xg) <= 1e-10
+    vg = O.mps_to_discrete_function(xg); vo = O.mps_to_discrete_function(xo)
+    assert np.linalg.norm(Am @ vg - bv) <= 1.05 * np.linalg.norm(Am @ vo - bv) + 1e-13
