@@ -217,7 +217,7 @@ def run_ours(args):
     xo = hx
     for i in range(e2e_steps):
         xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
-                           x0_canonical=True, ctx=ctx, return_info=True)
+                           x0_canonical=True, ctx=ctx, return_info=True, host_order="F")
         hx = xo   # chained like the device-resident steps: the e2e leg covers the same sweeps as `value`
     e2e_t = (time.perf_counter() - t0) / max(e2e_steps, 1)
     h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)

@@ -63,7 +63,7 @@ def _params(nsweeps, maxdim, mindim, cutoff, solver, a0, a1, tol, krylovdim, max
 
 def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,
              maxiter=10, ishermitian=False, normalize=False, outputlevel=0, fixed_matvecs=None, x0_canonical=False,
-             ctx=None, return_info=False, on_device=False):
+             ctx=None, return_info=False, on_device=False, host_order="C"):
     """`linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter, ishermitian)`
     -- solves (a0 + a1 A) x = b by two-site sweeps with a local GMRES
     (reference examples/airy_equation/src/linsolve.jl:24-34; call sites airy_equation.jl:429, src/eigsolve_target.jl:4).
@@ -83,7 +83,7 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
             dA.free()
         if fb:
             db.free()
-    out = dx if on_device else dx.download()
+    out = dx if on_device else dx.download(order=host_order)
     if not on_device:
         dx.free()
     if return_info:

@@ -56,15 +56,16 @@ class DeviceMPS:
         check(self.ctx.handle, lib.qtt_mps_dims(self.handle, out))
         return list(out)
 
-    def download(self):
-        """Host cores, shape (chi_l, 2, chi_r)."""
+    def download(self, order="C"):
+        """Host cores, shape (chi_l, 2, chi_r).  order="F" returns the column-major buffers the C ABI filled (what a Julia
+        caller gets: no host-side transpose); order="C" makes C-contiguous copies."""
         chi = self.dims()
         n = len(chi) - 1
         dt = np.complex128 if self.is_complex else np.float64
         bufs = [np.empty((chi[j], 2, chi[j + 1]), dtype=dt, order="F") for j in range(n)]
         ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
         check(self.ctx.handle, lib.qtt_mps_download(self.handle, ptrs))
-        return [np.ascontiguousarray(b) for b in bufs]
+        return bufs if order == "F" else [np.ascontiguousarray(b) for b in bufs]
 
     def clone(self):
         out = C.c_void_p()

@@ -297,7 +297,7 @@ static void upload_core(Ctx* ctx, DBuf& dst, const void* host, int nd, const int
     permute(ctx, re, dst.p, nd, rdims, perm);
     permute(ctx, im, dst.p + n, nd, rdims, perm);
   }
-  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  // no synchronisation here: the staging blocks return to the stream-ordered pool, the caller syncs once per chain
 }
 
 int qtt_mps_upload(qtt_ctx* ctx, int n, const int64_t* chi, const void* const* cores, int dtype, qtt_mps** out) {
@@ -317,6 +317,7 @@ int qtt_mps_upload(qtt_ctx* ctx, int n, const int64_t* chi, const void* const* c
       int perm[3] = {2, 1, 0};
       upload_core(ctx, m->core[j], cores[j], 3, dims, perm, dtype);
     }
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));  // host arrays are only borrowed for the duration of the call
   } catch (...) { delete m; throw; }
   *out = m;
   QTT_CATCH(ctx)
@@ -339,6 +340,7 @@ int qtt_mpo_upload(qtt_ctx* ctx, int n, const int64_t* w, const void* const* cor
       int perm[4] = {3, 2, 1, 0};
       upload_core(ctx, m->core[j], cores[j], 4, dims, perm, dtype);
     }
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
   } catch (...) { delete m; throw; }
   *out = m;
   QTT_CATCH(ctx)
@@ -363,10 +365,10 @@ int qtt_mps_download(const qtt_mps* x, void* const* cores_out) {
   QTT_TRY(ctx)
   QTT_REQUIRE(x && cores_out, "qtt_mps_download: bad arguments");
   QTT_CUDA(cudaSetDevice(ctx->device));
+  Scratch sc;  // staging for all cores; one synchronisation at the end
   for (int j = 0; j < x->n; ++j) {
     const int64_t a = x->chi[j], c = x->chi[j + 1];
     const size_t n = (size_t)a * 2 * c;
-    Scratch sc;
     int64_t rdims[3] = {a, 2, c};  // device [a][s][c] -> row-major [c][s][a] == col-major (a, s, c)
     int perm[3] = {2, 1, 0};
     if (x->dtype == QTT_F64) {
@@ -382,8 +384,8 @@ int qtt_mps_download(const qtt_mps* x, void* const* cores_out) {
       interleave(ctx, re, im, il, n);
       QTT_CUDA(cudaMemcpyAsync(cores_out[j], il, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
   QTT_CATCH(ctx)
 }
 
