@@ -193,6 +193,7 @@ struct Cgs2Args {
   unsigned* bar;    // monotonic barrier counter
   unsigned epoch;   // counter value at which this launch starts
   int per;          // slice length per CTA (even)
+  int kstash;       // the CTA's slices of V[0..kstash) are kept in shared memory after the first pass (read from L2 once, not 4x)
   int post;         // 0: store h1, h2, nrm2 only; 1: GMRES update; 2: Lanczos column
   double a0, a1, tol;
   volatile double* hstat;
@@ -217,7 +218,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 }
 
 // partial[b][i] = sum over the CTA's slice of V[i][e] * ws[e], all k vectors, 8 at a time (8 x M loads in flight)
-__device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, size_t s0, int n2, double* red /*[nwarps][64]*/,
+// MODE 0: V from L2, the first kstash (a multiple of 8) slices are also stashed in shared memory;
+// MODE 1: the stashed slices come from shared memory, the rest from L2.  Groups of 8 vectors are uniform (all stashed
+// or none), so the eight loads of a group are issued back to back before the FMAs.
+template <int MODE>
+__device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, double* vs, size_t s0, int n2, double* red /*[nwarps][64]*/,
                                            double* part_b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthr = blockDim.x, nwarps = nthr >> 5;
@@ -225,14 +230,30 @@ __device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, 
     double acc[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-    for (int t2 = tid; t2 < n2; t2 += nthr) {
-      const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
-      const double* vp = a.V + s0 + 2 * (size_t)t2;
+    if (MODE == 1 && i0 < a.kstash) {
+      for (int t2 = tid; t2 < n2; t2 += nthr) {
+        const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
+        const double* vp = vs + (size_t)i0 * a.per + 2 * t2;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (i0 + u < a.k) {
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len));
+        for (int u = 0; u < 8; ++u) {
+          const double2 v = *reinterpret_cast<const double2*>(vp + (size_t)u * a.per);
           acc[u] += v.x * wv.x + v.y * wv.y;
+        }
+      }
+    } else {
+      const bool st = (MODE == 0) && (i0 < a.kstash);
+      for (int t2 = tid; t2 < n2; t2 += nthr) {
+        const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
+        const double* vp = a.V + s0 + 2 * (size_t)t2 + (size_t)i0 * a.len;
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)u * a.len)) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += v[u].x * wv.x + v[u].y * wv.y;
+        if (st) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<double2*>(vs + (size_t)(i0 + u) * a.per + 2 * t2) = v[u];
         }
       }
     }
@@ -250,29 +271,46 @@ __device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, 
   }
 }
 
-// h[i] = sum_b part[b][i] in a fixed order (4 lanes per coefficient), result in shared memory
+// h[i] = sum_b part[b][i] in a fixed order, result in shared memory.  8 lanes per coefficient; every lane first issues
+// ALL its loads (independent, one L2 latency in total) and only then adds them up -- a dependent load-add chain over
+// 148 partials costs ~5 us per reduction, which was most of the fixed cost of the step.
 __device__ __forceinline__ void reduce_partials(const double* part, int k, int G, double* h_s) {
   const int tid = threadIdx.x;
-  const int i = tid >> 2, sub = tid & 3;
-  double s = 0.0;
-  if (i < k)
-    for (int b = sub; b < G; b += 4) s += __ldcg(part + (size_t)b * 64 + i);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (i < k && sub == 0) h_s[i] = s;
+  for (int c0 = 0; c0 < k; c0 += (int)(blockDim.x >> 3)) {
+    const int i = c0 + (tid >> 3), sub = tid & 7;
+    double v[20];
+#pragma unroll
+    for (int u = 0; u < 20; ++u) {
+      const int b = sub + 8 * u;
+      v[u] = (i < k && b < G) ? __ldcg(part + (size_t)b * 64 + i) : 0.0;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < 20; ++u) s += v[u];
+    for (int b = sub + 160; b < G; b += 8) s += (i < k) ? __ldcg(part + (size_t)b * 64 + i) : 0.0;  // G > 160 (not on B200)
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (i < k && sub == 0) h_s[i] = s;
+  }
   __syncthreads();
 }
 
-__device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, size_t s0, int n2, const double* h_s) {
+__device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, const double* vs, size_t s0, int n2, const double* h_s) {
   const int nthr = blockDim.x;
   for (int t2 = threadIdx.x; t2 < n2; t2 += nthr) {
     double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
     const double* vp = a.V + s0 + 2 * (size_t)t2;
     for (int i0 = 0; i0 < a.k; i0 += 8) {
       double2 v[8];
+      if (i0 < a.kstash) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u < a.k) v[u] = __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len));
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2*>(vs + (size_t)(i0 + u) * a.per + 2 * t2);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len)) : make_double2(0.0, 0.0);
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
         if (i0 + u < a.k) {
@@ -285,7 +323,6 @@ __device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, size_
   }
 }
 
-
 constexpr int FT_MAX = 512;
 __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   extern __shared__ double dyn[];
@@ -293,6 +330,7 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   double* red = dyn + a.per;       // [32][64]
   double* h1 = red + 32 * 64;      // [64]
   double* h2 = h1 + 64;            // [64]
+  double* vs = h2 + 64;            // [kstash][per] stashed slices of V
   __shared__ double nred[FT_MAX / 32];
   __shared__ double s_n2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,15 +349,15 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   double* P1 = a.part;
   double* P2 = a.part + (size_t)G * 64;
   double* P3 = a.part + (size_t)2 * G * 64;
-  slice_dots(a, ws, s0, n2, red, P1 + (size_t)b * 64);
+  slice_dots<0>(a, ws, vs, s0, n2, red, P1 + (size_t)b * 64);
   grid_barrier(a.bar, a.epoch + (unsigned)G);
   reduce_partials(P1, a.k, G, h1);
-  slice_axpys(a, ws, s0, n2, h1);
+  slice_axpys(a, ws, vs, s0, n2, h1);
   __syncthreads();
-  slice_dots(a, ws, s0, n2, red, P2 + (size_t)b * 64);
+  slice_dots<1>(a, ws, vs, s0, n2, red, P2 + (size_t)b * 64);
   grid_barrier(a.bar, a.epoch + 2u * (unsigned)G);
   reduce_partials(P2, a.k, G, h2);
-  slice_axpys(a, ws, s0, n2, h2);
+  slice_axpys(a, ws, vs, s0, n2, h2);
   __syncthreads();
   double nacc = 0.0;
   for (int t2 = tid; t2 < n2; t2 += nthr) {
@@ -453,10 +491,23 @@ bool kry_cgs2_fused_ok(const Ctx* ctx, size_t len) {
 void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, double* vnext, double* S, int off_h1, int off_h2,
                     int off_nres2, int off_done, int post, double a0, double a1, double tol, volatile double* hstat) {
   QTT_REQUIRE(k >= 1 && k <= 64, "kry_cgs2_fused: k out of range");
-  const int G = ctx->sms;
+  // one CTA per >= 1024 elements: short vectors (edge / mid bonds) use few CTAs, whose grid barriers are cheaper
+  static const int min_per = getenv("QTT_CGS2_MINPER") ? atoi(getenv("QTT_CGS2_MINPER")) : 1024;
+  int G = (int)((len + min_per - 1) / min_per);
+  if (G > ctx->sms) G = ctx->sms;
+  if (G < 1) G = 1;
   size_t per = (len + G - 1) / G;
   per = (per + 1) & ~size_t(1);
-  const size_t smem = (per + 32 * 64 + 128) * sizeof(double);
+  const size_t base = per + 32 * 64 + 128;  // doubles: w slice, reduction scratch, h1, h2
+  static const bool stash = !(getenv("QTT_CGS2_STASH") && atoi(getenv("QTT_CGS2_STASH")) == 0);
+  int kstash = 0;
+  if (stash) {
+    const size_t room = (size_t)(200 * 1024) / sizeof(double) - base;
+    kstash = (int)(room / per);
+    if (kstash > k) kstash = k;
+    kstash &= ~7;  // whole groups of 8 vectors
+  }
+  const size_t smem = (base + (size_t)kstash * per) * sizeof(double);
   static const int fthreads = getenv("QTT_CGS2_THREADS") ? atoi(getenv("QTT_CGS2_THREADS")) : 512;
   static size_t configured = 0;
   if (smem > configured) {
@@ -469,9 +520,11 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   a.bar = ctx->d_sync + 4;
   a.epoch = ctx->bar_epoch;
   a.per = (int)per;
+  a.kstash = kstash;
   a.post = post;
   a.a0 = a0; a.a1 = a1; a.tol = tol; a.hstat = hstat;
   a.off_h1 = off_h1; a.off_h2 = off_h2; a.off_nres2 = off_nres2; a.off_done = off_done;
+  // cooperative launch: the grid barriers need every CTA resident (measured: no extra launch cost over <<< >>>)
   void* args[] = {&a};
   QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
   ctx->launches++;
