@@ -128,7 +128,8 @@ typedef struct {
  * body examples/airy_equation/src/linsolve.jl:24-34).  x is updated in place.  per_sweep: nsweeps entries or NULL. */
 QTT_API int qtt_linsolve(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* b, qtt_mps* x_inout, const qtt_sweep_params* p, qtt_sweep_info* per_sweep);
 /* `dmrg_target(A, psi0; target_eigenvalue, nsweeps, maxdim, cutoff)` (reference src/dmrg_target.jl:1-12)
- * with the Krylov local solver the reference sketches at :14-21 / src/eigsolve_target.jl:2-9. */
+ * with the Krylov local solvers the reference sketches at :14-21: p->solver = QTT_SOLVER_LANCZOS (Ritz value nearest target) or
+ * QTT_SOLVER_SHIFT_INVERT (`eigsolve_target`, src/eigsolve_target.jl:2-9; fixed_matvecs must be 0). */
 QTT_API int qtt_dmrg_target(qtt_ctx* ctx, const qtt_mpo* A, qtt_mps* psi_inout, const qtt_sweep_params* p, qtt_sweep_info* per_sweep);
 /* enable per-phase CUDA-event timing inside the sweeps (adds one event pair per phase per bond) */
 QTT_API int qtt_set_profiling(qtt_ctx* ctx, int enabled);

@@ -12,7 +12,7 @@ from .chains import DeviceMPS, DeviceMPO
 
 __all__ = ["linsolve", "dmrg_target", "apply", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
-           "SOLVER_GMRES", "SOLVER_LANCZOS"]
+           "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT"]
 
 SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT = 0, 1, 2
 
@@ -93,14 +93,17 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
 
 def dmrg_target(A, psi0, *, target_eigenvalue, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-12, krylovdim=30,
                 maxiter=1, normalize=True, outputlevel=0, fixed_matvecs=None, x0_canonical=False, ctx=None,
-                return_info=False, on_device=False):
+                return_info=False, on_device=False, local_solver="lanczos"):
     """`dmrg_target(A, psi0; target_eigenvalue, nsweeps, maxdim, cutoff, ...)` (reference src/dmrg_target.jl:1-12) with
     the Krylov local solver the reference sketches at :14-21 (dense `eigen` of the (4 chi^2)^2 effective operator is
-    infeasible beyond chi ~ 64): restarted Lanczos, Ritz value nearest `target_eigenvalue`."""
+    infeasible beyond chi ~ 64).  local_solver="lanczos": restarted Lanczos, Ritz value nearest `target_eigenvalue` (extremal
+    targets); local_solver="shift_invert": `eigsolve_target` (reference src/eigsolve_target.jl:2-9) =
+    eigsolve(x -> linsolve(P, x, x, -target)), which also resolves interior eigenvalues."""
+    solver = {"lanczos": SOLVER_LANCZOS, "shift_invert": SOLVER_SHIFT_INVERT}[local_solver]
     ctx = ctx or default_context()
     dA, fa = _as_dev_mpo(A, ctx)
     dx = psi0.clone() if isinstance(psi0, DeviceMPS) else DeviceMPS(psi0, ctx)
-    p, keep = _params(nsweeps, maxdim, mindim, cutoff, SOLVER_LANCZOS, 0.0, 1.0, tol, krylovdim, maxiter, fixed_matvecs,
+    p, keep = _params(nsweeps, maxdim, mindim, cutoff, solver, 0.0, 1.0, tol, krylovdim, maxiter, fixed_matvecs,
                       normalize, outputlevel, target_eigenvalue, x0_canonical)
     infos = (SweepInfo * max(p.nsweeps, 1))()
     try:

@@ -58,8 +58,8 @@ struct KrylovWork {
   double* r = nullptr;
 };
 
-void read_scalars(Ctx* ctx, int off, int n, double* out) {
-  QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + H_READ, ctx->d_scal + off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+void read_scalars(Ctx* ctx, const double* S, int off, int n, double* out) {
+  QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + H_READ, S + off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   QTT_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; ++i) out[i] = ctx->h_scal[H_READ + i];
 }
@@ -68,8 +68,8 @@ void read_scalars(Ctx* ctx, int off, int n, double* out) {
 // Orthogonalisation is CGS2 (two classical Gram-Schmidt passes = 2 multi-dots + 2 multi-axpys), numerically equivalent
 // to KrylovKit's ModifiedGramSchmidt2 but with one reduction per pass instead of one per basis vector.
 void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, size_t len, double a0, double a1, double tol, int kd,
-                 int maxiter, bool fixed, KrylovWork& ws, LocalStats& st) {
-  double* S = ctx->d_scal;
+                 int maxiter, bool fixed, KrylovWork& ws, LocalStats& st, double* S = nullptr) {
+  if (!S) S = ctx->d_scal;
   volatile double* hstat = ctx->h_scal;
   auto vec = [&](int i) { return ws.V + (size_t)i * len; };
   const bool fused = kry_cgs2_fused_ok(ctx, len);
@@ -80,7 +80,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
   double beta = 0.0;
   if (!fixed) {
     double v;
-    read_scalars(ctx, S_R0N2, 1, &v);
+    read_scalars(ctx, S, S_R0N2, 1, &v);
     beta = sqrt(v);
     st.resid = beta;
     if (beta < tol) { st.converged = 1; return; }
@@ -116,7 +116,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
     int kfin = kd;
     if (!fixed) {
       double v[8];
-      read_scalars(ctx, 0, 8, v);
+      read_scalars(ctx, S, 0, 8, v);
       kfin = (int)v[S_K];
       beta = v[S_BETA];
       st.resid = beta;
@@ -137,7 +137,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
       kry_axpby(ctx, len, 1.0, beff, -a0, x, -a1, ws.w, ws.r);
       kry_nrm2sq(ctx, ws.r, len, S + S_R0N2);
       double v;
-      read_scalars(ctx, S_R0N2, 1, &v);
+      read_scalars(ctx, S, S_R0N2, 1, &v);
       beta = sqrt(v);
       st.resid = beta;
       if (beta < tol) { st.converged = 1; return; }
@@ -150,7 +150,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
 // single-warp cyclic Jacobi kernel; the Ritz vector nearest `target` is assembled with one multi-axpy.
 __global__ void lanczos_store_col_kernel(double* S, int k, int ld) { lanczos_step_scalars(S, k, ld); }
 
-__global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, double target, double* ritz_coef) {
+__global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, double target, int which, double* ritz_coef) {
   const int k = (int)S[S_K];
   // cyclic Jacobi eigen-decomposition of the k x k symmetric T in shared memory (k <= 62); lane-parallel row/col updates
   extern __shared__ double ritz_sm[];
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, dou
   __syncwarp();
   if (lane == 0) {
     int best = 0;
-    double bd = fabs(A[0][0] - target);
+    double bd = which ? -fabs(A[0][0]) : fabs(A[0][0] - target);
     for (int j = 1; j < k; ++j) {
-      double d = fabs(A[j][j] - target);
+      double d = which ? -fabs(A[j][j]) : fabs(A[j][j] - target);
       if (d < bd) { bd = d; best = j; }
     }
     S[S_THETA] = A[best][best];
@@ -220,12 +220,25 @@ __global__ void __launch_bounds__(32) ritz_kernel(double* S, int kd, int ld, dou
   for (int j = lane; j < kd; j += 32) ritz_coef[j] = j < k ? Q[j][best] : 0.0;
 }
 
+// which = 0: Ritz value nearest `target`; which = 1: largest magnitude (KrylovKit :LM, used by the shift-invert solver)
 void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double target, double tol, int kd, int maxiter, bool fixed,
-                   KrylovWork& ws, LocalStats& st) {
-  double* S = ctx->d_scal;
+                   KrylovWork& ws, LocalStats& st, double* S = nullptr, int which = 0, bool check_each = false) {
+  if (!S) S = ctx->d_scal;
   auto vec = [&](int i) { return ws.V + (size_t)i * len; };
   const bool fused = kry_cgs2_fused_ok(ctx, len);
+  auto run_ritz = [&]() {
+    constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      QTT_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRitzSmem));
+      configured = true;
+    }
+    ritz_kernel<<<1, 32, kRitzSmem, ctx->stream>>>(S, kd, 64, target, which, S + OFF_YK);
+    check_launch(ctx, "ritz");
+  };
   for (int it = 0; it < maxiter; ++it) {
+    int kused = kd;
+    bool early = false;
     kry_nrm2sq(ctx, x, len, S + S_R0N2);
     set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
     check_launch(ctx, "set_scalars");
@@ -245,22 +258,22 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
         check_launch(ctx, "lanczos_store_col");
         if (k < kd) kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
       }
-    }
-    {
-      constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
-      static bool configured = false;
-      if (!configured) {
-        QTT_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRitzSmem));
-        configured = true;
+      kused = k;
+      if (check_each && k >= 2 && k < kd) {
+        // expensive operator (shift-invert: one inner solve per application): test the Ritz pair after every expansion,
+        // as KrylovKit's eigsolve does
+        run_ritz();
+        double v[8];
+        read_scalars(ctx, S, 0, 8, v);
+        if (v[S_BETA] < tol || v[S_DONE] != 0.0) { early = true; break; }
       }
-      ritz_kernel<<<1, 32, kRitzSmem, ctx->stream>>>(S, kd, 64, target, S + OFF_YK);
     }
-    check_launch(ctx, "ritz");
+    if (!early) run_ritz();
     QTT_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
-    kry_axpys(ctx, ws.V, kd, len, S + OFF_YK, x, 1.0);
+    kry_axpys(ctx, ws.V, kused, len, S + OFF_YK, x, 1.0);
     if (fixed) { st.resid = 0.0; return; }
     double v[8];
-    read_scalars(ctx, 0, 8, v);
+    read_scalars(ctx, S, 0, 8, v);
     st.resid = v[S_BETA];
     st.theta = v[S_THETA];
     if (v[S_BETA] < tol) { st.converged = 1; return; }
@@ -392,7 +405,9 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   QTT_REQUIRE(kd >= 1 && kd <= KD_MAX, "krylovdim must be in [1, %d]", KD_MAX);
   const int maxiter = P.maxiter > 0 ? P.maxiter : 1;
   const bool is_lin = (P.solver == QTT_SOLVER_GMRES);
-  QTT_REQUIRE(is_lin || P.solver == QTT_SOLVER_LANCZOS, "solver kind %d not available in this build", P.solver);
+  QTT_REQUIRE(is_lin || P.solver == QTT_SOLVER_LANCZOS || P.solver == QTT_SOLVER_SHIFT_INVERT, "unknown solver kind %d", P.solver);
+  const bool shift_invert = (P.solver == QTT_SOLVER_SHIFT_INVERT);
+  QTT_REQUIRE(!(shift_invert && fixed), "fixed_matvecs is not defined for the shift-invert solver");
   QTT_REQUIRE(!is_lin || b, "linsolve needs a right-hand side");
 
   // QTT_TRACE=1 (with profiling enabled): per-bond phase timings on stderr; QTT_DUMP="sweep,dir,bond,path" saves that bond's phi
@@ -467,7 +482,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const int chil = (int)x.chi[j], chim = (int)x.chi[j + 1], chir = (int)x.chi[j + 2];
           const int wl = (int)A.w[j], wm = (int)A.w[j + 1], wr = (int)A.w[j + 2];
           const size_t len = (size_t)4 * chil * chir;
-          size_t need = (len * (size_t)(kd + 1 + 12) + matvec2_scratch(chil, chir, wl, wr) + (size_t)16 * wl * wr + 65536) * sizeof(double);
+          size_t need = (len * (size_t)(2 * (kd + 1) + 16) + matvec2_scratch(chil, chir, wl, wr) + (size_t)16 * wl * wr + 65536) * sizeof(double);
           need += (size_t)256 * (kd + 24);
           ctx->ensure_arena(need);
           size_t mark = ctx->arena.mark();
@@ -506,6 +521,22 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               } else {
                 gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws, st);
               }
+            } else if (shift_invert) {
+              // `eigsolve_target` (reference src/eigsolve_target.jl:2-9) as the local solver (src/dmrg_target.jl:14-21):
+              // eigsolve(x -> linsolve(P, x, x, -target)), dominant eigenpair of the inverse.  The inner GMRES uses the default
+              // scalar block, the outer Lanczos a second one.
+              KrylovWork wi;
+              wi.V = ctx->arena.alloc(len * (size_t)(kdl + 1));
+              wi.w = ctx->arena.alloc(len);
+              wi.r = ctx->arena.alloc(len);
+              MatvecFn finv = [&](const double* in, double* out) {
+                QTT_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * len, cudaMemcpyDeviceToDevice, ctx->stream));  // x0 = b = in
+                LocalStats si;
+                gmres_local(ctx, mv, in, out, len, -P.target, 1.0, P.tol, kdl, maxiter, false, wi, si);
+                st.matvecs += si.matvecs - 1;  // lanczos_local counts one application per call
+              };
+              lanczos_local(ctx, finv, phi, len, 0.0, P.tol, kdl, maxiter, false, ws, st, ctx->d_scal + 8192, 1, true);
+              info.energy = (st.theta != 0.0) ? P.target + 1.0 / st.theta : P.target;
             } else {
               lanczos_local(ctx, mv, phi, len, P.target, P.tol, kdl, maxiter, fixed, ws, st);
               info.energy = st.theta;

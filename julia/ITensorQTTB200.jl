@@ -54,6 +54,7 @@ end
 
 const QTT_SOLVER_GMRES = Int32(0)
 const QTT_SOLVER_LANCZOS = Int32(1)
+const QTT_SOLVER_SHIFT_INVERT = Int32(2)   # `eigsolve_target` (reference src/eigsolve_target.jl:2-9) as the local solver
 
 struct QttError <: Exception
   code::Int
@@ -218,7 +219,7 @@ Reference src/dmrg_target.jl:1-12 with the Krylov local solver sketched at :14-2
 (4 chi^2)^2 effective operator does not exist beyond chi ~ 64).
 """
 function dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim=typemax(Int32), mindim=1, cutoff=1e-16, tol=1e-12,
-                     krylovdim=30, maxiter=1, outputlevel=0, ctx::Context=context())
+                     krylovdim=30, maxiter=1, outputlevel=0, local_solver=QTT_SOLVER_LANCZOS, ctx::Context=context())
   hA = upload(ctx, A); hx = upload(ctx, psi0)
   md = sweepvec(Int32, min.(maxdim, typemax(Int32)), nsweeps)
   mn = sweepvec(Int32, mindim, nsweeps)
@@ -226,7 +227,7 @@ function dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim=typem
   infos = Vector{QttSweepInfo}(undef, nsweeps)
   try
     GC.@preserve md mn co begin
-      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), QTT_SOLVER_LANCZOS, 0.0, 1.0, tol, krylovdim, maxiter,
+      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), local_solver, 0.0, 1.0, tol, krylovdim, maxiter,
                              0, 1, outputlevel, target_eigenvalue, 0, 0))
       check(ctx, ccall((:qtt_dmrg_target, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{QttSweepParams}, Ptr{QttSweepInfo}),
                        ctx.handle, hA, hx, p, infos))

@@ -108,3 +108,21 @@ def test_multi_kernel_path_large_bonds(lib):
     assert O.fidelity_defect(xo, xg) <= 1e-10
     vg = O.mps_to_discrete_function(xg); vo = O.mps_to_discrete_function(xo)
     assert np.linalg.norm(Am @ vg - bv) <= 1.05 * np.linalg.norm(Am @ vo - bv) + 1e-13
+
+
+def test_dmrg_target_shift_invert_interior_eigenvalue(lib):
+    """`eigsolve_target` as the local solver (reference src/eigsolve_target.jl:2-9, src/dmrg_target.jl:14-21): an INTERIOR
+    eigenvalue of the Laplacian (the Helmholtz mode nk = 2, helmholtz_equation.jl:48), which a Ritz-value pick cannot isolate."""
+    n = 7
+    Al = O.laplacian_mpo(n, 1.0)
+    Lm = O.laplacian_matrix(2 ** n)
+    D, U = np.linalg.eigh(Lm)
+    target = O.helmholtz_lambda(n, 2) * 1.001          # near, not at, an eigenvalue
+    near = int(np.argmin(np.abs(D - target)))
+    psi0 = O.vec_to_mps(U[:, near] + 0.3 * np.random.default_rng(0).standard_normal(2 ** n), cutoff=1e-12, maxdim=6)
+    psi, info = lib.dmrg_target(Al, psi0, target_eigenvalue=target, nsweeps=3, maxdim=8, cutoff=1e-13, krylovdim=20, maxiter=3,
+                                tol=1e-10, return_info=True, local_solver="shift_invert")
+    v = O.mps_to_discrete_function(psi)
+    v /= np.linalg.norm(v)
+    assert 1 - abs(v @ U[:, near]) < 1e-8
+    assert abs(info[-1]["energy"] - D[near]) < 1e-8 * abs(D[near])
