@@ -198,7 +198,11 @@ def run_ours(args):
     achieved = f_mv / (mv_ms * 1e-3) / 1e12
     sweep_mv_tflops = infos[-1]["flops_matvec"] / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the kernel pair from the round-1 `ncu --set full` capture
+                # (profiles/r01_ncu_full_matvec_cgs2.md: 3.70 MB + 7.88 MB read, 0 written, cold cache) -- algorithmic operand
+                # bytes 7.3 MB + the T2 intermediate (6.3 MB) that matvec_a hands to matvec_b through L2
+                "traffic": 11.58e6 if chi == 256 else None,
                 "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_kernel (L.v DMMA GEMM + W12 register epilogue) + "
                           "matvec_b_kernel (T2.R DMMA GEMM, in-CTA split-K), the pair timed back to back with CUDA events on "
                           "the library's stream" % chi,

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
   if (tid == 0) ctl->nbp = 0;
   if (ctl->done) return;
   const int r0 = ctl->r;
-  const int serial = ctl->serial;
+  const int serial = ctl->serial + 1;  // this panel's serial number (published below; qr_apply reads it)
+  __syncthreads();
+  if (tid == 0) ctl->serial = serial;
   // |Z|_F^2 once (the initial norms are the full row norms)
   if (ctl->F2 < 0.0) {
     __shared__ double red[PANEL_W];
@@ -342,7 +344,6 @@ __global__ void __launch_bounds__(PANEL_T) qr_apply_generic_kernel(double* __res
   }
 }
 
-__global__ void qr_next_panel_kernel(QrCtl* ctl) { ctl->serial += 1; }
 
 // Y[j][i] = SE[i][j] for j < r (tiled transpose); columns [q, qd) of Y are zero padding.
 __global__ void build_y_kernel(const double* __restrict__ SE, int q, int p, int ldp, int qd, int ldy, double* __restrict__ Y, const QrCtl* ctl) {
@@ -1103,8 +1104,6 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     else if (p <= 1024) qr_apply_kernel<32><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
     else qr_apply_generic_kernel<<<agrid, PANEL_T, 0, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
     check_launch(ctx, "qr_apply");
-    qr_next_panel_kernel<<<1, 1, 0, ctx->stream>>>(ctl);
-    check_launch(ctx, "qr_next_panel");
   }
   const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
   cudaEvent_t evq = nullptr, evj = nullptr;
