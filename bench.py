@@ -216,9 +216,14 @@ def run_ours(args):
     # outside the timed region and re-homed in pinned memory
     hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x_start.download())
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
+    xo = hx
+    if e2e_steps:
+        # one untimed pass of the same call: first-use costs of the host path (device blocks entering the caching
+        # allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
+        q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
+                   x0_canonical=True, ctx=ctx, return_info=True, host_order="F")
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    xo = hx
     for i in range(e2e_steps):
         xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
                            x0_canonical=True, ctx=ctx, return_info=True, host_order="F")

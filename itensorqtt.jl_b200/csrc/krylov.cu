@@ -343,6 +343,19 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   // the done flag of the PREVIOUS step decides whether v_next is written as zeros (the flag of this step is only
   // committed by CTA 0 after the last barrier; see sweep.cu for why lagging by one step is safe)
   const bool dead = a.S != nullptr && a.S[a.off_done] != 0.0;
+  // CTA 0 stages the Givens rotations / rhs element of the earlier steps for the on-chip scalar update at the end
+  __shared__ double gcs[64], gss[64];
+  __shared__ double s_yprev, s_r0n2;
+  if (b == 0 && a.S != nullptr && a.post == 1) {
+    if (tid < 64) {
+      gcs[tid] = a.S[kscal::OFF_GC + tid];
+      gss[tid] = a.S[kscal::OFF_GS + tid];
+    }
+    if (tid == 0) {
+      s_yprev = a.k >= 2 ? a.S[kscal::OFF_Y + a.k - 1] : 0.0;
+      s_r0n2 = a.S[kscal::S_R0N2];
+    }
+  }
   for (int t2 = tid; t2 < n2; t2 += nthr)
     *reinterpret_cast<double2*>(ws + 2 * t2) = __ldcg(reinterpret_cast<const double2*>(a.w + s0 + 2 * (size_t)t2));
   __syncthreads();
@@ -394,10 +407,12 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
       a.S[a.off_h2 + tid] = h2[tid];
     }
     if (tid == 0) a.S[a.off_nres2] = n2sq;
-    __syncthreads();
-    if (tid == 0) {
-      if (a.post == 1) kscal::gmres_step_scalars(a.S, a.k, a.a0, a.a1, a.tol, 64, a.hstat);
-      else if (a.post == 2) kscal::lanczos_step_scalars(a.S, a.k, 64);
+    if (a.post == 1) {
+      if (tid == 0)
+        kscal::gmres_step_scalars_onchip(a.S, a.k, a.a0, a.a1, a.tol, 64, a.hstat, h1, h2, gcs, gss, s_yprev, s_r0n2, dead ? 1.0 : 0.0, n2sq);
+    } else {
+      __syncthreads();
+      if (tid == 0 && a.post == 2) kscal::lanczos_step_scalars(a.S, a.k, 64);
     }
   }
 }

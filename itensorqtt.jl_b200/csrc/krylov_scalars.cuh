@@ -71,6 +71,52 @@ __device__ inline void gmres_step_scalars(double* S, int k, double a0, double a1
   }
 }
 
+// Same update with the inputs already on chip (the fused CGS2 kernel): h = h1 + h2 and the stored rotations gc/gs come
+// from shared memory, the running Hessenberg column lives in registers, and global memory only receives fire-and-forget
+// stores.  The plain version above pays a store -> load round trip per rotation (~0.25 us each) when S is in global memory.
+__device__ inline void gmres_step_scalars_onchip(double* S, int k, double a0, double a1, double tol, int ld, volatile double* hstat,
+                                                 const double* h1s, const double* h2s, const double* gcs, const double* gss, double y_prev,
+                                                 double r0n2, double done_prev, double nres2) {
+  if (done_prev != 0.0) return;
+  const double nres = sqrt(nres2);
+  S[S_NRES] = nres;
+  double* Rm = S + OFF_R;
+  double hn2 = nres * nres;
+  double cur = 0.0;
+  for (int i = 0; i < k; ++i) {
+    const double h = h1s[i] + h2s[i];
+    hn2 += h * h;
+    const double col = (i == k - 1) ? (a0 + a1 * h) : (a1 * h);
+    if (i == 0) {
+      cur = col;
+    } else {
+      const double t1 = cur, t2 = col;
+      Rm[(i - 1) * ld + (k - 1)] = gcs[i - 1] * t1 + gss[i - 1] * t2;
+      cur = -gss[i - 1] * t1 + gcs[i - 1] * t2;
+    }
+  }
+  const bool breakdown = !(nres > 1e-13 * sqrt(hn2));
+  double c, s, r;
+  givens(cur, a1 * nres, c, s, r);
+  S[OFF_GC + k - 1] = c;
+  S[OFF_GS + k - 1] = s;
+  Rm[(k - 1) * ld + (k - 1)] = r;
+  const double yk = (k == 1) ? sqrt(r0n2) : y_prev;
+  S[OFF_Y + k - 1] = c * yk;
+  S[OFF_Y + k] = -s * yk;
+  const double beta = fabs(s * yk);
+  S[S_BETA] = beta;
+  S[S_K] = (double)k;
+  const double done = (!(beta > tol) || breakdown) ? 1.0 : 0.0;
+  if (done != 0.0) S[S_DONE] = 1.0;
+  if (hstat) {
+    hstat[H_K] = (double)k;
+    hstat[H_BETA] = beta;
+    hstat[H_DONE] = done;
+    __threadfence_system();
+  }
+}
+
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
 // k >= 0: use k columns.  k < 0: use the device-side step count S_K and zero-fill yk up to kd = -k.
 __device__ inline void gmres_solve_scalars(double* S, int k_or_neg_kd, int ld) {

@@ -31,7 +31,15 @@ __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, doub
 }
 
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
-__global__ void gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) { gmres_solve_scalars(S, k_or_neg_kd, ld); }
+// single-thread back substitution on a shared-memory copy of the scalar block (global-memory latency made it 49 us)
+__global__ void __launch_bounds__(256) gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) {
+  extern __shared__ double Ss[];
+  for (int i = threadIdx.x; i < OFF_END; i += blockDim.x) Ss[i] = S[i];
+  __syncthreads();
+  if (threadIdx.x == 0) gmres_solve_scalars(Ss, k_or_neg_kd, ld);
+  __syncthreads();
+  for (int i = threadIdx.x; i < OFF_R; i += blockDim.x) S[i] = Ss[i];  // only the vectors change (yk, coef, S_R0N2)
+}
 
 __global__ void set_scalars_kernel(double* p, int n, double v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,7 +131,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
     }
     // fixed mode: the device-side step count (S_K < kd after an early breakdown) is used by the kernel itself; the
     // coefficients beyond it are zero and the corresponding basis vectors were written as zeros.
-    gmres_solve_kernel<<<1, 1, 0, ctx->stream>>>(S, fixed ? -kd : kfin, 64);
+    gmres_solve_kernel<<<1, 256, OFF_END * sizeof(double), ctx->stream>>>(S, fixed ? -kd : kfin, 64);
     check_launch(ctx, "gmres_solve");
     kry_axpys(ctx, ws.V, kfin, len, S + OFF_YK, x, 1.0);
     if (fixed) return;
