@@ -193,6 +193,8 @@ struct Cgs2Args {
   unsigned* bar;    // monotonic barrier counter
   unsigned epoch;   // counter value at which this launch starts
   int per;          // slice length per CTA (even)
+  double eta2;      // DGKS threshold eta^2 (0: always reorthogonalise); see cgs2_fused_kernel
+  int* counters;    // optional [2]: steps, steps that needed the second pass (trace)
   int kstash;       // the CTA's slices of V[0..kstash) are kept in shared memory after the first pass (read from L2 once, not 4x)
   int post;         // 0: store h1, h2, nrm2 only; 1: GMRES update; 2: Lanczos column
   double a0, a1, tol;
@@ -362,29 +364,62 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   double* P1 = a.part;
   double* P2 = a.part + (size_t)G * 64;
   double* P3 = a.part + (size_t)2 * G * 64;
+  // |w|^2 of the incoming vector (column 63 of the partial row), for the reorthogonalisation test
+  auto block_norm2 = [&](double* dst) {
+    double nacc = 0.0;
+    for (int t2 = tid; t2 < n2; t2 += nthr) {
+      const double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
+      nacc += x.x * x.x + x.y * x.y;
+    }
+    nacc = warp_sum(nacc);
+    if (lane == 0) nred[warp] = nacc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int wdx = 0; wdx < nwarps; ++wdx) s += nred[wdx];
+      __stcg(dst, s);
+    }
+  };
+  if (a.eta2 > 0.0) block_norm2(P1 + (size_t)b * 64 + 63);
   slice_dots<0>(a, ws, vs, s0, n2, red, P1 + (size_t)b * 64);
   grid_barrier(a.bar, a.epoch + (unsigned)G);
   reduce_partials(P1, a.k, G, h1);
+  // DGKS test (Daniel-Gragg-Kaufman-Stewart): the second Gram-Schmidt pass is only needed when the first one cancelled
+  // most of w.  |w'|^2 is ESTIMATED by Pythagoras, |w|^2 - |h1|^2, for the decision only (identical in every CTA: the
+  // inputs are the fixed-order reductions); the norm that is used afterwards is computed from the actual vector.
+  bool second = true;
+  if (a.eta2 > 0.0) {
+    if (warp == 0) {
+      double sw = 0.0;
+      for (int bb = lane; bb < G; bb += 32) sw += __ldcg(P1 + (size_t)bb * 64 + 63);
+      sw = warp_sum(sw);
+      double sh = 0.0;
+      for (int i = lane; i < a.k; i += 32) sh += h1[i] * h1[i];
+      sh = warp_sum(sh);
+      if (lane == 0) s_n2 = ((sw - sh) >= a.eta2 * sw) ? 0.0 : 1.0;
+    }
+    __syncthreads();
+    second = (s_n2 != 0.0);
+    __syncthreads();
+  }
   slice_axpys(a, ws, vs, s0, n2, h1);
   __syncthreads();
-  slice_dots<1>(a, ws, vs, s0, n2, red, P2 + (size_t)b * 64);
-  grid_barrier(a.bar, a.epoch + 2u * (unsigned)G);
-  reduce_partials(P2, a.k, G, h2);
-  slice_axpys(a, ws, vs, s0, n2, h2);
-  __syncthreads();
-  double nacc = 0.0;
-  for (int t2 = tid; t2 < n2; t2 += nthr) {
-    const double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
-    nacc += x.x * x.x + x.y * x.y;
+  if (second) {
+    slice_dots<1>(a, ws, vs, s0, n2, red, P2 + (size_t)b * 64);
+    grid_barrier(a.bar, a.epoch + 2u * (unsigned)G);
+    reduce_partials(P2, a.k, G, h2);
+    slice_axpys(a, ws, vs, s0, n2, h2);
+    __syncthreads();
+  } else {
+    if (tid < 64) h2[tid] = 0.0;
+    // keep the barrier counter in step with the host's bookkeeping (3 arrivals per CTA per launch)
+    if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;\n" ::"l"(a.bar) : "memory");
   }
-  nacc = warp_sum(nacc);
-  if (lane == 0) nred[warp] = nacc;
-  __syncthreads();
-  if (tid == 0) {
-    double s = 0.0;
-    for (int wdx = 0; wdx < nwarps; ++wdx) s += nred[wdx];
-    __stcg(P3 + b, s);
+  if (a.counters && b == 0 && tid == 0) {
+    atomicAdd(a.counters, 1);
+    if (second) atomicAdd(a.counters + 1, 1);
   }
+  block_norm2(P3 + b);
   grid_barrier(a.bar, a.epoch + 3u * (unsigned)G);
   if (warp == 0) {
     double s = 0.0;
@@ -536,6 +571,9 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   a.epoch = ctx->bar_epoch;
   a.per = (int)per;
   a.kstash = kstash;
+  static const double eta = getenv("QTT_DGKS_ETA") ? atof(getenv("QTT_DGKS_ETA")) : 0.0;
+  a.eta2 = eta * eta;
+  a.counters = nullptr;
   a.post = post;
   a.a0 = a0; a.a1 = a1; a.tol = tol; a.hstat = hstat;
   a.off_h1 = off_h1; a.off_h2 = off_h2; a.off_nres2 = off_nres2; a.off_done = off_done;

@@ -1141,14 +1141,14 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   static const bool one_warp = getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "onewarp";
   const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
   static const bool blocked = !(getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "pair");
-  if (!one_warp && blocked && half <= 512 && kmax >= 16) {
+  if (!one_warp && blocked && half <= 1024 && kmax >= 16) {
     // block-cyclic kernel: one CTA per pair of JB-row blocks
     static const int jb = getenv("QTT_JB") ? atoi(getenv("QTT_JB")) : 4;
     const int nbk = (((kmax + jb - 1) / jb) + 1) & ~1;
     int bgrid = nbk / 2;
     if (bgrid > ctx->sms) bgrid = ctx->sms;
     const size_t smem = (size_t)2 * jb * ldy * sizeof(double);
-    if (jb == 8 && smem <= 200 * 1024) {
+    if (jb == 8 && smem <= 200 * 1024 && half <= 512) {
       if (half <= 64) launch_jq_block<1, 8>(ctx, a, bgrid, smem);
       else if (half <= 128) launch_jq_block<2, 8>(ctx, a, bgrid, smem);
       else if (half <= 256) launch_jq_block<4, 8>(ctx, a, bgrid, smem);
@@ -1161,7 +1161,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
       if (half <= 64) launch_jq_block<1, 4>(ctx, a, g4, smem4);
       else if (half <= 128) launch_jq_block<2, 4>(ctx, a, g4, smem4);
       else if (half <= 256) launch_jq_block<4, 4>(ctx, a, g4, smem4);
-      else launch_jq_block<8, 4>(ctx, a, g4, smem4);
+      else if (half <= 512) launch_jq_block<8, 4>(ctx, a, g4, smem4);
+      else launch_jq_block<16, 4>(ctx, a, g4, smem4);  // chi = 512: rows of 1024 + 1024 doubles
     }
   } else if (!one_warp && half <= 512) {
     if (half <= 64) launch_jq_pair<1>(ctx, a, grid);
