@@ -150,21 +150,19 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
   }
   __syncthreads();
   int nfin = 0;
+  // residual norms |row[r0:]|^2 of the panel rows; afterwards they are refreshed inside the update pass of every step
+  for (int u = warp; u < nsel; u += PANEL_W) {
+    const double* row = P + (size_t)u * ldp;
+    double acc = 0.0;
+    for (int c = r0 + lane; c < p; c += 32) acc += row[c] * row[c];
+    acc = warp_sum(acc);
+    if (lane == 0) res[u] = acc;
+  }
   for (int t = 0; t < nsel; ++t) {
     const int j = r0 + t;
-    // residual norms of the not yet processed panel rows
-    for (int u = warp; u < nsel; u += PANEL_W) {
-      double acc = -1.0;
-      if (!proc[u]) {
-        acc = 0.0;
-        const double* row = P + (size_t)u * ldp;
-        for (int c = j + lane; c < p; c += 32) acc += row[c] * row[c];
-        acc = warp_sum(acc);
-      }
-      if (lane == 0) res[u] = acc;
-    }
-    __syncthreads();
+    __syncthreads();  // res[] of the previous update pass (or the initial norms) is complete
     if (warp == 0) {
+      // in-panel pivot: the largest residual among the unprocessed rows (processed rows carry -1)
       double best = lane < nsel ? res[lane] : -1.0;
       int bi = lane;
 #pragma unroll
@@ -173,34 +171,34 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
-      if (lane == 0) {
-        if (!(best > thr)) s_stop = 1;
-        s_piv = bi;
+      if (!(best > thr)) {
+        if (lane == 0) s_stop = 1;
+      } else {
+        // dlarfg: beta = -sign(x_j) |x[j:]|, tau = (beta - x_j) / beta, v = x[j+1:] / (x_j - beta), v_j = 1
+        double* x = P + (size_t)bi * ldp;
+        const double xj = x[j];
+        const double nrmx = sqrt(best);
+        const double beta = -copysign(nrmx, xj);
+        const double tau = (beta - xj) / beta;
+        const double scale = 1.0 / (xj - beta);
+        for (int c = j + 1 + lane; c < p; c += 32) x[c] *= scale;
+        __syncwarp();
+        if (lane == 0) {
+          x[j] = 1.0;
+          beta_s[t] = beta;
+          tau_s[t] = tau;
+          s_tau = tau;
+          s_piv = bi;
+          order[t] = bi;
+          proc[bi] = 1;
+          res[bi] = -1.0;
+        }
       }
     }
     __syncthreads();
     if (s_stop) break;
     const int piv = s_piv;
-    double* x = P + (size_t)piv * ldp;
-    if (warp == 0) {
-      // dlarfg: beta = -sign(x_j) |x[j:]|, tau = (beta - x_j) / beta, v = x[j+1:] / (x_j - beta), v_j = 1
-      const double xj = x[j];
-      const double nrmx = sqrt(res[piv]);
-      const double beta = -copysign(nrmx, xj);
-      const double tau = (beta - xj) / beta;
-      const double scale = 1.0 / (xj - beta);
-      for (int c = j + 1 + lane; c < p; c += 32) x[c] *= scale;
-      __syncwarp();
-      if (lane == 0) {
-        x[j] = 1.0;
-        beta_s[t] = beta;
-        tau_s[t] = tau;
-        s_tau = tau;
-        order[t] = piv;
-        proc[piv] = 1;
-      }
-    }
-    __syncthreads();
+    const double* x = P + (size_t)piv * ldp;
     const double tau = s_tau;
     for (int u = warp; u < nsel; u += PANEL_W) {
       if (proc[u]) continue;
@@ -208,11 +206,18 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
       double d = 0.0;
       for (int c = j + lane; c < p; c += 32) d += row[c] * x[c];
       d = warp_sum(d) * tau;
-      for (int c = j + lane; c < p; c += 32) row[c] -= d * x[c];
+      double acc = 0.0;  // residual for the next step: |row[j+1:]|^2 after the reflection
+      for (int c = j + lane; c < p; c += 32) {
+        const double v = row[c] - d * x[c];
+        row[c] = v;
+        if (c > j) acc += v * v;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) res[u] = acc;
     }
     nfin = t + 1;
-    __syncthreads();
   }
+  __syncthreads();
   // ---- write back: reflectors, finished rows of R^T, the partially updated leftovers
   for (int t = warp; t < nb; t += PANEL_W) {
     double* vrow = Vp + (size_t)t * ldp;
