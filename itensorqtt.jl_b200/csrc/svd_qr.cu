@@ -250,6 +250,228 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
   }
 }
 
+// Register-resident panel factorisation (p <= 32 * NPL): every warp keeps its RPW panel rows in registers (element c
+// lives in lane c % 32, slot c / 32), the current reflector is broadcast through shared memory, finished rows of R^T and
+// the reflectors go straight to global memory.  The shared-memory version above pays a dependent LDS per element in four
+// unrolled-by-one loops per step (4.6 us per reflector, measured); here a step is two short register passes.
+constexpr int RP_T = 256;          // threads of the register-resident panel kernel: 8 warps, up to 255 registers each
+constexpr int RP_W = RP_T / 32;
+template <int NPL, int RPW>
+__global__ void __launch_bounds__(RP_T) qr_panel_reg_kernel(double* __restrict__ SE, int q, int p, int ldp, int rmax, double zero_tol2,
+                                                               const double* __restrict__ norms, int* __restrict__ rowstate,
+                                                               int* __restrict__ inpanel, double* __restrict__ Vp,
+                                                               double* __restrict__ taus, QrCtl* ctl) {
+  constexpr int NBP = RP_W * RPW;  // panel width
+  extern __shared__ double sm[];
+  double* xs = sm;                    // [32 * NPL] current reflector (zeros left of j)
+  double* nrm = sm + 32 * NPL;        // [q] candidate norms
+  __shared__ int sel[NBP];
+  __shared__ int proc[NBP];
+  __shared__ double res[NBP];
+  __shared__ double tau_s[NBP];
+  __shared__ int s_nsel, s_piv, s_stop;
+  __shared__ double s_tau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) ctl->nbp = 0;
+  if (ctl->done) return;
+  const int r0 = ctl->r;
+  const int serial = ctl->serial + 1;
+  __syncthreads();
+  if (tid == 0) ctl->serial = serial;
+  if (ctl->F2 < 0.0) {
+    __shared__ double red[RP_W];
+    double acc = 0.0;
+    for (int i = tid; i < q; i += RP_T) acc += norms[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < RP_W; ++k) t += red[k];
+      ctl->F2 = t;
+      ctl->thr = zero_tol2 * t;
+    }
+    __syncthreads();
+  }
+  const double thr = ctl->thr;
+  int want = rmax - r0;
+  if (want > NBP) want = NBP;
+  for (int i = tid; i < q; i += RP_T) nrm[i] = (rowstate[i] == 0) ? norms[i] : -1.0;
+  if (tid < NBP) { sel[tid] = -1; proc[tid] = 0; res[tid] = -1.0; }
+  if (tid == 0) { s_nsel = 0; s_stop = 0; }
+  __syncthreads();
+  for (int i = tid; i < q; i += RP_T) {
+    const double ni = nrm[i];
+    if (!(ni > thr)) continue;
+    int rank = 0;
+    for (int j = 0; j < q; ++j) {
+      const double nj = nrm[j];
+      rank += (nj > ni) || (nj == ni && j < i);
+    }
+    if (rank < want) {
+      sel[rank] = i;
+      atomicAdd(&s_nsel, 1);
+    }
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+  if (nsel == 0) {
+    if (tid == 0) ctl->done = 1;
+    return;
+  }
+  // ---- rows into registers: warp w owns panel slots w, w + 16, ...
+  double row[RPW][NPL];
+  bool mine[RPW], done_row[RPW];
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int u = warp + RP_W * rr;
+    mine[rr] = u < nsel;
+    done_row[rr] = false;
+    const double* src = SE + (size_t)(mine[rr] ? sel[u] : 0) * ldp;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const int c = lane + 32 * k;
+      const double v = (mine[rr] && c < p) ? src[c] : 0.0;
+      row[rr][k] = v;
+      if (c >= r0) acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && mine[rr]) res[u] = acc;
+  }
+  int nfin = 0;
+  for (int t = 0; t < nsel; ++t) {
+    const int j = r0 + t;
+    __syncthreads();  // res[] complete
+    if (warp == 0) {
+      double best = lane < nsel ? res[lane] : -1.0;
+      int bi = lane;
+      if (NBP > 32 && lane + 32 < nsel && res[lane + 32] > best) { best = res[lane + 32]; bi = lane + 32; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        if (!(best > thr)) s_stop = 1;
+        s_piv = bi;
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
+    const int piv = s_piv;
+    // the owner warp turns its row into the reflector, publishes it, and writes the finished row of R^T / the reflector
+    if (warp == (piv % RP_W)) {
+      const int rr_p = piv / RP_W;
+      // copy of the pivot row chosen with selects (a dynamically indexed register array would be demoted to local memory)
+      double pr[NPL];
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        double v = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) v = (rr == rr_p) ? row[rr][k] : v;
+        pr[k] = v;
+      }
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) done_row[rr] = done_row[rr] || (rr == rr_p);
+      // x_j sits in lane j % 32, slot j / 32
+      double xj = 0.0;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) xj = (k == j / 32) ? pr[k] : xj;
+      xj = __shfl_sync(0xffffffffu, xj, j % 32);
+      const double nrmx = sqrt(res[piv]);
+      const double beta = -copysign(nrmx, xj);
+      const double tau = (beta - xj) / beta;
+      const double scale = 1.0 / (xj - beta);
+      double* dst = SE + (size_t)sel[piv] * ldp;
+      double* vrow = Vp + (size_t)t * ldp;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        const double v = c > j ? pr[k] * scale : (c == j ? 1.0 : 0.0);
+        xs[c] = v;
+        if (c < ldp) {
+          vrow[c] = (c < p) ? v : 0.0;
+          if (c >= r0) dst[c] = c < j ? pr[k] : (c == j ? beta : 0.0);
+        }
+      }
+      if (lane == 0) {
+        tau_s[t] = tau;
+        s_tau = tau;
+        proc[piv] = 1;
+        res[piv] = -1.0;
+        rowstate[sel[piv]] = 1;
+      }
+    }
+    __syncthreads();
+    const double tau = s_tau;
+    double xv[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) xv[k] = xs[lane + 32 * k];
+    // all rows of the warp are processed together: RPW independent accumulation chains hide the DFMA latency
+    double d[RPW], acc[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) d[rr] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k)
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) d[rr] += row[rr][k] * xv[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) d[rr] += __shfl_xor_sync(0xffffffffu, d[rr], o);
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      d[rr] = (mine[rr] && !done_row[rr]) ? d[rr] * tau : 0.0;  // finished / absent rows stay untouched
+      acc[rr] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const int c = lane + 32 * k;
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const double v = row[rr][k] - d[rr] * xv[k];
+        row[rr][k] = v;
+        acc[rr] += (c > j) ? v * v : 0.0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr)
+        if (mine[rr] && !done_row[rr]) res[warp + RP_W * rr] = acc[rr];
+    }
+    nfin = t + 1;
+  }
+  __syncthreads();
+  // leftovers (rows the threshold stopped): partially updated, written back; all panel rows are tagged with the serial
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int u = warp + RP_W * rr;
+    if (!mine[rr]) continue;
+    if (!done_row[rr]) {
+      double* dst = SE + (size_t)sel[u] * ldp;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c >= r0 && c < ldp) dst[c] = row[rr][k];
+      }
+    }
+    if (lane == 0) inpanel[sel[u]] = serial;
+  }
+  if (tid < nfin) taus[tid] = tau_s[tid];
+  if (tid == 0) {
+    ctl->r = r0 + nfin;
+    ctl->nbp = nfin;
+    if (r0 + nfin >= rmax) ctl->done = 1;
+  }
+}
+
 // Applies the panel's reflectors (in order) from the right to every row of SE that was not in the panel, and refreshes
 // the residual norms |z_i[r:]|^2 of all unprocessed rows.  NPL = row elements per lane.
 template <int NPL>
@@ -1102,7 +1324,16 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;
   if (agrid > ctx->sms) agrid = ctx->sms;
   for (int pn = 0; pn < npanels; ++pn) {
-    qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    static const bool reg_panel = !(getenv("QTT_QR_PANEL") && std::string(getenv("QTT_QR_PANEL")) == "smem");
+    if (reg_panel && p <= 256) {
+      qr_panel_reg_kernel<8, 4><<<1, 256, (256 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    } else if (reg_panel && p <= 512) {
+      qr_panel_reg_kernel<16, 4><<<1, 256, (512 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    } else if (reg_panel && p <= 1024) {
+      qr_panel_reg_kernel<32, 2><<<1, 256, (1024 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    } else {
+      qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
+    }
     check_launch(ctx, "qr_panel");
     if (p <= 256) qr_apply_kernel<8><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
     else if (p <= 512) qr_apply_kernel<16><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
