@@ -1324,7 +1324,9 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;
   if (agrid > ctx->sms) agrid = ctx->sms;
   for (int pn = 0; pn < npanels; ++pn) {
-    static const bool reg_panel = !(getenv("QTT_QR_PANEL") && std::string(getenv("QTT_QR_PANEL")) == "smem");
+    // the register-resident panel kernel is opt-in (QTT_QR_PANEL=reg): measured 35 / 74 / 128 ms of split time per sweep
+    // (bench sweeps 3 / 4 / 5) against 32 / 69 / 127 ms with the shared-memory panel kernel
+    static const bool reg_panel = getenv("QTT_QR_PANEL") && std::string(getenv("QTT_QR_PANEL")) == "reg";
     if (reg_panel && p <= 256) {
       qr_panel_reg_kernel<8, 4><<<1, 256, (256 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
     } else if (reg_panel && p <= 512) {
