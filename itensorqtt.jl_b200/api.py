@@ -10,7 +10,7 @@ import numpy as np
 from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
 from .chains import DeviceMPS, DeviceMPO
 
-__all__ = ["linsolve", "dmrg_target", "apply", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+__all__ = ["linsolve", "dmrg_target", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
            "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT"]
 
@@ -281,3 +281,51 @@ def krylov_op(op, V, w, h=None, reps=1, ctx=None):
     ms = C.c_float(0)
     check(ctx.handle, lib.qtt_krylov_op(ctx.handle, int(op), dptr(V), nvec, ln, dptr(w), dptr(hh), dptr(out), int(reps), C.byref(ms)))
     return w, hh, out[0], ms.value
+
+
+# ---------------------------------------------------------------- prolongation / retraction / multigrid (host glue around qtt_apply)
+def _host_cores(psi):
+    return psi.download() if isinstance(psi, DeviceMPS) else [np.asarray(c) for c in psi]
+
+
+def prolongate(psi, nnew=1, *, cutoff=1e-8, maxdim=None, ctx=None):
+    """`prolongate(psi, s_new; cutoff=1e-8)` (reference src/prolongation.jl:29-60, 1-D): append a dummy site, apply the
+    prolongation MPO (linear interpolation onto the grid with one more bit) on the GPU; repeated `nnew` times."""
+    from .operators import prolongation_mpo
+    cores = _host_cores(psi)
+    for _ in range(nnew):
+        dummy = np.zeros((1, 2, 1), dtype=cores[0].dtype)
+        dummy[0, 0, 0] = 1.0
+        cores = apply(prolongation_mpo(len(cores) + 1), list(cores) + [dummy], cutoff=cutoff, maxdim=maxdim, ctx=ctx)
+    return cores
+
+
+def retract(psi, nretract=1, *, cutoff=1e-8, maxdim=None, ctx=None):
+    """`retract(psi, nretract=1; cutoff=1e-8)` (reference src/prolongation.jl:66-102, 1-D): apply the transposed prolongation
+    MPO on the GPU, absorb the dummy output site into its neighbour, divide by 2."""
+    from .operators import retraction_mpo
+    cores = _host_cores(psi)
+    for _ in range(nretract):
+        out = apply(retraction_mpo(len(cores)), cores, cutoff=cutoff, maxdim=maxdim, ctx=ctx)
+        last = out[-1][:, 0, :]
+        out[-2] = np.tensordot(out[-2], last, axes=([2], [0]))
+        cores = [c.copy() for c in out[:-1]]
+        cores[0] = 0.5 * cores[0]
+    return cores
+
+
+def multigrid_linsolve(problem, levels, x0, a0=0, a1=1, *, prolong_cutoff=1e-15, ctx=None, return_history=False, **kw):
+    """The multigrid driver of the reference examples (examples/airy_equation/airy_equation.jl:453-516,
+    examples/helmholtz_equation/helmholtz_equation.jl:153-224): solve on n bits, prolongate the solution to n + 1 bits
+    (`prolongate(u, s_new; cutoff=1e-15)`, :497) and use it as the starting state of the next level.
+    problem(n) -> (A, b); levels: increasing bit counts; x0: starting MPS on levels[0] bits; kw: `linsolve` keywords."""
+    x = x0
+    hist = []
+    for i, n in enumerate(levels):
+        A, b = problem(n)
+        if i > 0:
+            x = prolongate(x, n - levels[i - 1], cutoff=prolong_cutoff, ctx=ctx)
+        x, info = linsolve(A, b, x, a0, a1, ctx=ctx, return_info=True, **kw)
+        hist.append(dict(n=n, maxlinkdim=info[-1]["maxlinkdim"], matvecs=sum(s["matvecs"] for s in info),
+                         residual=sqeuclidean_normalized((A, x), b, ctx=ctx) if (a0 == 0 and a1 == 1) else None))
+    return (x, hist) if return_history else x

@@ -251,17 +251,29 @@ function apply_mpo(A::MPO, psi::MPS; cutoff=1e-13, maxdim=0, mindim=1, ctx::Cont
   end
 end
 
-# reference src/dft.jl:121-133: the chain reversal stays here
+# reference src/dft.jl:121-133: the chain reversal stays here.  The reference rebuilds the DFT MPO on every call (:123);
+# its dense cores only depend on (n, cutoff), so they are cached here and re-labelled with the caller's site indices.
+const _dft_cache = Dict{Tuple{Int,Float64,Bool},MPO}()
+function cached_dft_mpo(s; cutoff, inverse=false)
+  key = (length(s), Float64(cutoff), inverse)
+  F = get!(_dft_cache, key) do
+    inverse ? idft_mpo(s; cutoff) : dft_mpo(s; cutoff)
+  end
+  s0 = [siteind(F, j; plev=0) for j in 1:length(F)]
+  return s0 == s ? F : replace_siteinds(F, s0, s)
+end
+replace_siteinds(F::MPO, old, new) = MPO([replaceinds(F[j], (old[j], old[j]') => (new[j], new[j]')) for j in 1:length(F)])
+
 function apply_dft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
   s = siteinds(psi)
-  F = dft_mpo(s; cutoff)
+  F = cached_dft_mpo(s; cutoff)
   phi = apply_mpo(F, psi; cutoff, kwargs...)
   return MPS(reverse([phi[j] for j in 1:length(phi)]))
 end
 
 function apply_idft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
   s = siteinds(psi)
-  F = idft_mpo(s; cutoff)
+  F = cached_dft_mpo(s; cutoff, inverse=true)
   phi = apply_mpo(F, psi; cutoff, kwargs...)
   return MPS(reverse([phi[j] for j in 1:length(phi)]))
 end

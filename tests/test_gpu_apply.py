@@ -116,3 +116,41 @@ def test_dft_apply_real_input_complex_operator_bond_dims(lib):
     assert max(O.linkdims(got)) <= max(O.linkdims(want)) + 1
     fw = dense(want)
     assert np.abs(dense(got) - fw).max() <= 1e-9 * np.abs(fw).max()
+
+
+def test_prolongate_and_retract_known_answers(lib):
+    """test/runtests.jl:184-215 ("Prolongation and retraction - 1-dimensional"): f(x) = sin(pi x) on 10, 11, 12 bits."""
+    f = lambda n: O.vec_to_mps(np.sin(np.pi * O.qtt_xrange(n, 0.0, 1.0)), cutoff=1e-15)
+    psi0, psi1, psi2 = f(10), f(11), f(12)
+    nrm = lambda a: np.linalg.norm(dense(a))
+    close = lambda a, b, rtol: np.linalg.norm(dense(a) - dense(b)) <= rtol * max(nrm(a), nrm(b))
+    assert close(lib.prolongate(psi1), psi2, 1e-6)              # prolongate by one
+    assert close(lib.prolongate(psi0, 2), psi2, 1e-6)           # prolongate by two
+    assert close(lib.retract(psi2), psi1, 1e-5)                 # retract by one
+    assert close(lib.retract(psi2, 2), psi0, 1e-5)              # retract by two
+    # the GPU path agrees with the oracle's apply-based restatement
+    assert close(lib.prolongate(psi1), O.prolongate(psi1), 1e-9) and close(lib.retract(psi2), O.retract(psi2), 1e-9)
+
+
+def test_multigrid_linsolve_airy(lib):
+    """Multigrid driver (examples/airy_equation/airy_equation.jl:453-516): the prolongated coarse solution is the starting
+    state of the next level; the final level reaches the dense solution."""
+    xi, xf = 1.0, 4.0
+    alpha = beta = 1 / np.sqrt(2)
+
+    def problem(n):
+        h = (xf - xi) / 2 ** n
+        return O.airy_mpo(n, xi, xf), O.boundary_value_mps(n, O.airy_solution(xi - h, alpha, beta), O.airy_solution(xf, alpha, beta))
+
+    x, hist = lib.multigrid_linsolve(problem, [4, 5, 6, 7, 8], O.random_mps(4, 4, 1), nsweeps=2, maxdim=16, cutoff=1e-13, tol=1e-12,
+                                     krylovdim=30, maxiter=10, return_history=True)
+    A, b = problem(8)
+    xd = np.linalg.solve(O.mpo_to_mat(A), dense(b))
+    v = dense(x)
+    assert np.linalg.norm(v - xd) <= 1e-5 * np.linalg.norm(xd)     # cutoff 1e-13 on sigma^2: ~3e-7 in norm
+    assert [h["n"] for h in hist] == [4, 5, 6, 7, 8] and abs(hist[-1]["residual"]) < 1e-9
+    # the prolongated coarse solution is already close to the fine one (what makes the warm start worthwhile)
+    A7, b7 = problem(7)
+    x7 = lib.linsolve(A7, b7, O.random_mps(7, 4, 1), nsweeps=3, maxdim=16, cutoff=1e-13, tol=1e-12, krylovdim=30, maxiter=10)
+    guess = dense(lib.prolongate(x7, cutoff=1e-15))
+    assert 1 - abs(guess @ xd) / np.linalg.norm(guess) / np.linalg.norm(xd) < 1e-3   # last point interpolates towards 0
