@@ -5,6 +5,7 @@
 // are bit-reproducible run to run).
 #include "common.cuh"
 #include "krylov_scalars.cuh"
+#include "device_utils.cuh"
 #include <cstdlib>
 
 namespace qtt {
@@ -14,11 +15,7 @@ constexpr int KT = 256;          // threads per CTA
 constexpr int EPT = 4;           // elements per thread per chunk
 constexpr int CHUNK = KT * EPT;  // 1024 elements per CTA iteration
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+using dev::warp_sum;
 
 // partial[cta][i] = sum over the CTA's elements of V[i][e] * w[e] for up to NV vectors at once (accumulators in
 // registers, ONE block-level reduction for all of them); the last CTA to arrive reduces the partials in a fixed order.
@@ -202,24 +199,8 @@ struct Cgs2Args {
   int off_h1, off_h2, off_nres2, off_done;
 };
 
-__device__ __forceinline__ unsigned ld_acq_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
-  return v;
-}
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) { dev::grid_arrive_wait(counter, target); }
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // one cumulative release-RED instead of membar + atomic (svd_qr.cu:grid_sync)
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-    while ((int)(ld_acq_u32(counter) - target) < 0) {
-    }
-  }
-  __syncthreads();
-}
-
-// partial[b][i] = sum over the CTA's slice of V[i][e] * ws[e], all k vectors, 8 at a time (8 x M loads in flight)
 // MODE 0: V from L2, the first kstash (a multiple of 8) slices are also stashed in shared memory;
 // MODE 1: the stashed slices come from shared memory, the rest from L2.  Groups of 8 vectors are uniform (all stashed
 // or none), so the eight loads of a group are issued back to back before the FMAs.

@@ -9,6 +9,7 @@
 // accumulated in a different order than on the DMMA path, so results agree to rounding, not bitwise.
 #include "common.cuh"
 #include "krylov_scalars.cuh"
+#include "device_utils.cuh"
 #include <cstdlib>
 
 namespace qtt {
@@ -33,11 +34,7 @@ struct SmallArgs {
   double* stats;       // out: [0] matvecs, [1] resid, [2] converged, [3] last S_BETA
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+using dev::warp_sum;
 
 struct Smem {
   double* L; double* R; double* W; double* v; double* w; double* T1; double* T2; double* S; double* h; double* red;

@@ -12,6 +12,7 @@
 // the truncation scan) is ONE cooperative persistent kernel with a monotonic-counter grid barrier between rounds, so
 // there is no host round trip until the kept rank is read back.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include <cstdlib>
 
 namespace qtt {
@@ -20,28 +21,9 @@ void permute(Ctx*, const double*, double*, int, const int64_t*, const int*);
 
 namespace {
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-    while (ld_acquire(counter) < target) {
-    }
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+using dev::warp_sum;
+using dev::ld_acquire;
+using dev::grid_sync;
 
 struct JacobiArgs {
   double* Zi;      // imaginary plane (same layout) or nullptr for real data
@@ -260,41 +242,11 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
-  // rank sort, descending, ties by index (stable)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.q; i += gridDim.x * blockDim.x) {
-    double ni = __ldcg(a.norms + i);
-    int rank = 0;
-    for (int j = 0; j < a.q; ++j) {
-      double nj = __ldcg(a.norms + j);
-      rank += (nj > ni) || (nj == ni && j < i);
-    }
-    a.perm[rank] = i;
-    a.sig2[rank] = ni;
-  }
+  dev::rank_sort_desc(a.norms, a.q, a.q, a.sig2, a.perm);
   grid_sync(a.sync, target);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // NDTensors.truncate! on P = sigma^2 descending
-    const int q = a.q;
-    int n = q;
-    double err = 0.0;
-    int maxdim = a.maxdim < q ? a.maxdim : q;
-    int mindim = a.mindim > 1 ? a.mindim : 1;
-    if (q > 1) {
-      while (n > maxdim) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      double scale = 0.0;
-      for (int i = 0; i < q; ++i) scale += __ldcg(a.sig2 + i);
-      if (scale == 0.0) scale = 1.0;
-      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      err /= scale;
-    }
-    if (n < 1) n = 1;
-    a.info[0] = n;
+    double err;
+    a.info[0] = dev::truncate_spectrum(a.sig2, a.q, a.cutoff, a.maxdim, a.mindim, &err);
     a.info[1] = sweeps;
     a.info[2] = converged;
     a.derr[0] = err;

@@ -17,11 +17,16 @@
 //   3. descending sort of sigma^2, NDTensors.truncate! rule, gather of the kept rows.
 // Everything is enqueued without a host round trip; only the kept rank is read back at the end.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include <cstdlib>
 #include <string>
 
 namespace qtt {
 namespace {
+
+using dev::warp_sum;
+using dev::ld_acquire;
+using dev::grid_sync;
 
 constexpr int NB = 32;          // panel width (reflectors per panel)
 constexpr int PANEL_T = 512;    // threads of the panel / apply kernels (16 warps)
@@ -36,12 +41,6 @@ struct QrCtl {
   double F2;    // |Z|_F^2
   double thr;   // zero threshold on squared norms
 };
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // SE rows [0,q) = Z (zero padded to ldp), rows [q, q+p) = identity; norms[i] = |z_i|^2
 __global__ void qr_init_kernel(const double* __restrict__ M, int q, int p, int ldp, double* __restrict__ SE, double* __restrict__ norms,
@@ -600,26 +599,6 @@ __global__ void build_y_kernel(const double* __restrict__ SE, int q, int p, int 
 }
 
 // ------------------------------------------------------------------ Jacobi on the rows of [R | Q^T]
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));
-  return v;
-}
-
-// Grid barrier on a monotonic counter (cooperative launch guarantees co-residency).  Arrival is ONE release-RED: the
-// release is cumulative over the CTA's stores ordered before it by bar.sync, so no separate membar round trip is paid;
-// the waiters poll with acquire loads.
-__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-    while (ld_acquire(counter) < target) {
-    }
-  }
-  __syncthreads();
-}
-
 struct JqArgs {
   double* Y;       // [rcap][ld]
   int ld, ndot;    // row stride / length; the rotation angles use columns [0, ndot)
@@ -774,46 +753,11 @@ __global__ void __launch_bounds__(64) jacobi_qr_kernel(JqArgs a) {
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
-  // rank sort, descending, ties by index; entries [q, kmax) of the spectrum are exact zeros
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
-    if (i < q) {
-      const double ni = __ldcg(a.norms + i);
-      int rank = 0;
-      for (int j = 0; j < q; ++j) {
-        const double nj = __ldcg(a.norms + j);
-        rank += (nj > ni) || (nj == ni && j < i);
-      }
-      a.perm[rank] = i;
-      a.sig2[rank] = ni;
-    } else {
-      a.perm[i] = -1;
-      a.sig2[i] = 0.0;
-    }
-  }
+  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
   grid_sync(a.sync, target);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // NDTensors.truncate! on P = sigma^2 descending
-    const int len = a.kmax;
-    int n = len;
-    double err = 0.0;
-    int maxdim = a.maxdim < len ? a.maxdim : len;
-    int mindim = a.mindim > 1 ? a.mindim : 1;
-    if (len > 1) {
-      while (n > maxdim) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      double scale = 0.0;
-      for (int i = 0; i < len; ++i) scale += __ldcg(a.sig2 + i);
-      if (scale == 0.0) scale = 1.0;
-      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      err /= scale;
-    }
-    if (n < 1) n = 1;
-    a.info[0] = n;
+    double err;
+    a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
     a.info[1] = sweeps;
     a.info[2] = converged;
     a.info[3] = q;
@@ -946,44 +890,11 @@ __global__ void __launch_bounds__(128) jacobi_qr_pair_kernel(JqArgs a) {
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
-    if (i < q) {
-      const double ni = __ldcg(a.norms + i);
-      int rank = 0;
-      for (int j = 0; j < q; ++j) {
-        const double nj = __ldcg(a.norms + j);
-        rank += (nj > ni) || (nj == ni && j < i);
-      }
-      a.perm[rank] = i;
-      a.sig2[rank] = ni;
-    } else {
-      a.perm[i] = -1;
-      a.sig2[i] = 0.0;
-    }
-  }
+  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
   grid_sync(a.sync, target);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int len = a.kmax;
-    int n = len;
-    double err = 0.0;
-    int maxdim = a.maxdim < len ? a.maxdim : len;
-    int mindim = a.mindim > 1 ? a.mindim : 1;
-    if (len > 1) {
-      while (n > maxdim) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      double scale = 0.0;
-      for (int i = 0; i < len; ++i) scale += __ldcg(a.sig2 + i);
-      if (scale == 0.0) scale = 1.0;
-      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      err /= scale;
-    }
-    if (n < 1) n = 1;
-    a.info[0] = n;
+    double err;
+    a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
     a.info[1] = sweeps;
     a.info[2] = converged;
     a.info[3] = q;
@@ -1188,44 +1099,11 @@ __global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.kmax; i += gridDim.x * blockDim.x) {
-    if (i < q) {
-      const double ni = __ldcg(a.norms + i);
-      int rank = 0;
-      for (int j = 0; j < q; ++j) {
-        const double nj = __ldcg(a.norms + j);
-        rank += (nj > ni) || (nj == ni && j < i);
-      }
-      a.perm[rank] = i;
-      a.sig2[rank] = ni;
-    } else {
-      a.perm[i] = -1;
-      a.sig2[i] = 0.0;
-    }
-  }
+  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
   grid_sync(a.sync, target);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int lenp = a.kmax;
-    int n = lenp;
-    double err = 0.0;
-    int maxdim = a.maxdim < lenp ? a.maxdim : lenp;
-    int mindim = a.mindim > 1 ? a.mindim : 1;
-    if (lenp > 1) {
-      while (n > maxdim) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      double scale = 0.0;
-      for (int i = 0; i < lenp; ++i) scale += __ldcg(a.sig2 + i);
-      if (scale == 0.0) scale = 1.0;
-      while (n > mindim && err + __ldcg(a.sig2 + n - 1) <= a.cutoff * scale) {
-        err += __ldcg(a.sig2 + n - 1);
-        --n;
-      }
-      err /= scale;
-    }
-    if (n < 1) n = 1;
-    a.info[0] = n;
+    double err;
+    a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
     a.info[1] = sweeps;
     a.info[2] = converged;
     a.info[3] = q;
