@@ -24,6 +24,7 @@
 namespace qtt {
 namespace {
 
+constexpr int JB = 4;  // rows per block of the block-cyclic Jacobi ordering (8 was measured slower)
 using dev::warp_sum;
 using dev::ld_acquire;
 using dev::grid_sync;
@@ -238,228 +239,6 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
       if (lane == 0) rowstate[sel[u]] = 1;
     } else {
       for (int c = r0 + lane; c < ldp; c += 32) dst[c] = row[c];
-    }
-    if (lane == 0) inpanel[sel[u]] = serial;
-  }
-  if (tid < nfin) taus[tid] = tau_s[tid];
-  if (tid == 0) {
-    ctl->r = r0 + nfin;
-    ctl->nbp = nfin;
-    if (r0 + nfin >= rmax) ctl->done = 1;
-  }
-}
-
-// Register-resident panel factorisation (p <= 32 * NPL): every warp keeps its RPW panel rows in registers (element c
-// lives in lane c % 32, slot c / 32), the current reflector is broadcast through shared memory, finished rows of R^T and
-// the reflectors go straight to global memory.  The shared-memory version above pays a dependent LDS per element in four
-// unrolled-by-one loops per step (4.6 us per reflector, measured); here a step is two short register passes.
-constexpr int RP_T = 256;          // threads of the register-resident panel kernel: 8 warps, up to 255 registers each
-constexpr int RP_W = RP_T / 32;
-template <int NPL, int RPW>
-__global__ void __launch_bounds__(RP_T) qr_panel_reg_kernel(double* __restrict__ SE, int q, int p, int ldp, int rmax, double zero_tol2,
-                                                               const double* __restrict__ norms, int* __restrict__ rowstate,
-                                                               int* __restrict__ inpanel, double* __restrict__ Vp,
-                                                               double* __restrict__ taus, QrCtl* ctl) {
-  constexpr int NBP = RP_W * RPW;  // panel width
-  extern __shared__ double sm[];
-  double* xs = sm;                    // [32 * NPL] current reflector (zeros left of j)
-  double* nrm = sm + 32 * NPL;        // [q] candidate norms
-  __shared__ int sel[NBP];
-  __shared__ int proc[NBP];
-  __shared__ double res[NBP];
-  __shared__ double tau_s[NBP];
-  __shared__ int s_nsel, s_piv, s_stop;
-  __shared__ double s_tau;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) ctl->nbp = 0;
-  if (ctl->done) return;
-  const int r0 = ctl->r;
-  const int serial = ctl->serial + 1;
-  __syncthreads();
-  if (tid == 0) ctl->serial = serial;
-  if (ctl->F2 < 0.0) {
-    __shared__ double red[RP_W];
-    double acc = 0.0;
-    for (int i = tid; i < q; i += RP_T) acc += norms[i];
-    acc = warp_sum(acc);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int k = 0; k < RP_W; ++k) t += red[k];
-      ctl->F2 = t;
-      ctl->thr = zero_tol2 * t;
-    }
-    __syncthreads();
-  }
-  const double thr = ctl->thr;
-  int want = rmax - r0;
-  if (want > NBP) want = NBP;
-  for (int i = tid; i < q; i += RP_T) nrm[i] = (rowstate[i] == 0) ? norms[i] : -1.0;
-  if (tid < NBP) { sel[tid] = -1; proc[tid] = 0; res[tid] = -1.0; }
-  if (tid == 0) { s_nsel = 0; s_stop = 0; }
-  __syncthreads();
-  for (int i = tid; i < q; i += RP_T) {
-    const double ni = nrm[i];
-    if (!(ni > thr)) continue;
-    int rank = 0;
-    for (int j = 0; j < q; ++j) {
-      const double nj = nrm[j];
-      rank += (nj > ni) || (nj == ni && j < i);
-    }
-    if (rank < want) {
-      sel[rank] = i;
-      atomicAdd(&s_nsel, 1);
-    }
-  }
-  __syncthreads();
-  const int nsel = s_nsel;
-  if (nsel == 0) {
-    if (tid == 0) ctl->done = 1;
-    return;
-  }
-  // ---- rows into registers: warp w owns panel slots w, w + 16, ...
-  double row[RPW][NPL];
-  bool mine[RPW], done_row[RPW];
-#pragma unroll
-  for (int rr = 0; rr < RPW; ++rr) {
-    const int u = warp + RP_W * rr;
-    mine[rr] = u < nsel;
-    done_row[rr] = false;
-    const double* src = SE + (size_t)(mine[rr] ? sel[u] : 0) * ldp;
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-      const int c = lane + 32 * k;
-      const double v = (mine[rr] && c < p) ? src[c] : 0.0;
-      row[rr][k] = v;
-      if (c >= r0) acc += v * v;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0 && mine[rr]) res[u] = acc;
-  }
-  int nfin = 0;
-  for (int t = 0; t < nsel; ++t) {
-    const int j = r0 + t;
-    __syncthreads();  // res[] complete
-    if (warp == 0) {
-      double best = lane < nsel ? res[lane] : -1.0;
-      int bi = lane;
-      if (NBP > 32 && lane + 32 < nsel && res[lane + 32] > best) { best = res[lane + 32]; bi = lane + 32; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (lane == 0) {
-        if (!(best > thr)) s_stop = 1;
-        s_piv = bi;
-      }
-    }
-    __syncthreads();
-    if (s_stop) break;
-    const int piv = s_piv;
-    // the owner warp turns its row into the reflector, publishes it, and writes the finished row of R^T / the reflector
-    if (warp == (piv % RP_W)) {
-      const int rr_p = piv / RP_W;
-      // copy of the pivot row chosen with selects (a dynamically indexed register array would be demoted to local memory)
-      double pr[NPL];
-#pragma unroll
-      for (int k = 0; k < NPL; ++k) {
-        double v = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) v = (rr == rr_p) ? row[rr][k] : v;
-        pr[k] = v;
-      }
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) done_row[rr] = done_row[rr] || (rr == rr_p);
-      // x_j sits in lane j % 32, slot j / 32
-      double xj = 0.0;
-#pragma unroll
-      for (int k = 0; k < NPL; ++k) xj = (k == j / 32) ? pr[k] : xj;
-      xj = __shfl_sync(0xffffffffu, xj, j % 32);
-      const double nrmx = sqrt(res[piv]);
-      const double beta = -copysign(nrmx, xj);
-      const double tau = (beta - xj) / beta;
-      const double scale = 1.0 / (xj - beta);
-      double* dst = SE + (size_t)sel[piv] * ldp;
-      double* vrow = Vp + (size_t)t * ldp;
-#pragma unroll
-      for (int k = 0; k < NPL; ++k) {
-        const int c = lane + 32 * k;
-        const double v = c > j ? pr[k] * scale : (c == j ? 1.0 : 0.0);
-        xs[c] = v;
-        if (c < ldp) {
-          vrow[c] = (c < p) ? v : 0.0;
-          if (c >= r0) dst[c] = c < j ? pr[k] : (c == j ? beta : 0.0);
-        }
-      }
-      if (lane == 0) {
-        tau_s[t] = tau;
-        s_tau = tau;
-        proc[piv] = 1;
-        res[piv] = -1.0;
-        rowstate[sel[piv]] = 1;
-      }
-    }
-    __syncthreads();
-    const double tau = s_tau;
-    double xv[NPL];
-#pragma unroll
-    for (int k = 0; k < NPL; ++k) xv[k] = xs[lane + 32 * k];
-    // all rows of the warp are processed together: RPW independent accumulation chains hide the DFMA latency
-    double d[RPW], acc[RPW];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) d[rr] = 0.0;
-#pragma unroll
-    for (int k = 0; k < NPL; ++k)
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) d[rr] += row[rr][k] * xv[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) d[rr] += __shfl_xor_sync(0xffffffffu, d[rr], o);
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      d[rr] = (mine[rr] && !done_row[rr]) ? d[rr] * tau : 0.0;  // finished / absent rows stay untouched
-      acc[rr] = 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-      const int c = lane + 32 * k;
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const double v = row[rr][k] - d[rr] * xv[k];
-        row[rr][k] = v;
-        acc[rr] += (c > j) ? v * v : 0.0;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], o);
-    if (lane == 0) {
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr)
-        if (mine[rr] && !done_row[rr]) res[warp + RP_W * rr] = acc[rr];
-    }
-    nfin = t + 1;
-  }
-  __syncthreads();
-  // leftovers (rows the threshold stopped): partially updated, written back; all panel rows are tagged with the serial
-#pragma unroll
-  for (int rr = 0; rr < RPW; ++rr) {
-    const int u = warp + RP_W * rr;
-    if (!mine[rr]) continue;
-    if (!done_row[rr]) {
-      double* dst = SE + (size_t)sel[u] * ldp;
-#pragma unroll
-      for (int k = 0; k < NPL; ++k) {
-        const int c = lane + 32 * k;
-        if (c >= r0 && c < ldp) dst[c] = row[rr][k];
-      }
     }
     if (lane == 0) inpanel[sel[u]] = serial;
   }
@@ -765,149 +544,10 @@ __global__ void __launch_bounds__(64) jacobi_qr_kernel(JqArgs a) {
   }
 }
 
-// ---- two warps per row pair (row parts <= 512 doubles) ------------------------------------------------------------
-// A pair slot is served by TWO warps: warp A owns the R part of the two rows (dot products, rotation angle), warp B the
-// carried Q^T part (loaded while A reduces), which halves the per-warp load/store time of a round (a round is latency
-// bound: 3.3 us with one warp per 1024-double row pair, measured).  Rounds are separated by the grid barrier.
-// A point-to-point variant (each slot waits only for its two neighbour slots through release/acquire flags, which is
-// all the round-robin data flow requires) was measured SLOWER than the grid barrier on B200 (random 512 x 512:
-// 42-57 ms vs 23 ms) and was dropped.
+// ---- helpers of the block-cyclic kernel ---------------------------------------------------------------------------
+// (Intermediate variants, measured and superseded -- one warp per pair with a grid barrier per round, two warps per pair,
+// point-to-point neighbour flags instead of the barrier, 8-row blocks -- are recorded in profiles/r01_svd_notes.md.)
 __device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
-
-template <int NC>
-__global__ void __launch_bounds__(128) jacobi_qr_pair_kernel(JqArgs a) {
-  __shared__ double cs_s[2][4];  // per slot-unit: c, s, rotate?
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int unit_in_cta = warp >> 1;
-  const int role = warp & 1;  // 0: R part (angles), 1: carried part
-  const int units = gridDim.x * 2;
-  const int unit = blockIdx.x * 2 + unit_in_cta;
-  const int q = a.ctl->r;
-  const double thr = a.ctl->thr;
-  const int qe = (q + 1) & ~1;
-  const int npairs = qe / 2, rounds = qe - 1;
-  const int c_lo = role == 0 ? 0 : a.ndot;
-  const int c_hi = role == 0 ? a.ndot : a.ld;
-  unsigned target = 0;
-  int sweeps = 0;
-  int converged = (q < 2) ? 1 : 0;
-  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
-    bool rotated = false;
-    for (int r = 0; r < rounds; ++r) {
-      for (int i = unit; i < npairs; i += units) {
-        int ia, ib;
-        if (i == 0) {
-          ia = r;
-          ib = qe - 1;
-        } else {
-          ia = (r + i) % (qe - 1);
-          ib = (r - i + (qe - 1)) % (qe - 1);
-        }
-        if (ia > ib) {
-          int tmp = ia;
-          ia = ib;
-          ib = tmp;
-        }
-        const bool live = (ia < q && ib < q);
-        if (live) {
-          double* ra = a.Y + (size_t)ia * a.ld + c_lo;
-          double* rb = a.Y + (size_t)ib * a.ld + c_lo;
-          const int len = c_hi - c_lo;
-          double2 za[NC], zb[NC];
-#pragma unroll
-          for (int k = 0; k < NC; ++k) {
-            const int col = 2 * lane + 64 * k;
-            if (col < len) {
-              za[k] = __ldcg(reinterpret_cast<const double2*>(ra + col));
-              zb[k] = __ldcg(reinterpret_cast<const double2*>(rb + col));
-            } else {
-              za[k] = make_double2(0.0, 0.0);
-              zb[k] = make_double2(0.0, 0.0);
-            }
-          }
-          if (role == 0) {
-            double alpha = 0.0, beta = 0.0, gamma = 0.0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-              alpha += za[k].x * za[k].x + za[k].y * za[k].y;
-              beta += zb[k].x * zb[k].x + zb[k].y * zb[k].y;
-              gamma += za[k].x * zb[k].x + za[k].y * zb[k].y;
-            }
-            alpha = warp_sum(alpha);
-            beta = warp_sum(beta);
-            gamma = warp_sum(gamma);
-            double c = 1.0, s = 0.0, rot = 0.0;
-            if ((alpha > thr) && (beta > thr)) {
-              const double lim = sqrt(alpha) * sqrt(beta);
-              if ((lim > 0.0) && (fabs(gamma) > a.tol * lim)) {
-                jrotation(alpha, beta, gamma, c, s);
-                rot = 1.0;
-              }
-            }
-            if (lane == 0) {
-              cs_s[unit_in_cta][0] = c;
-              cs_s[unit_in_cta][1] = s;
-              cs_s[unit_in_cta][2] = rot;
-            }
-          }
-          pair_bar(1 + unit_in_cta);
-          const double c = cs_s[unit_in_cta][0], s = cs_s[unit_in_cta][1];
-          const bool rot = cs_s[unit_in_cta][2] != 0.0;
-          if (rot) {
-            rotated = true;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-              const int col = 2 * lane + 64 * k;
-              if (col < len) {
-                __stcg(reinterpret_cast<double2*>(ra + col), make_double2(c * za[k].x - s * zb[k].x, c * za[k].y - s * zb[k].y));
-                __stcg(reinterpret_cast<double2*>(rb + col), make_double2(s * za[k].x + c * zb[k].x, s * za[k].y + c * zb[k].y));
-              }
-            }
-          }
-          if (npairs > units) pair_bar(1 + unit_in_cta);  // cs_s is reused by this unit's next slot of the round
-        }
-      }
-      grid_sync(a.sync, target);
-    }
-    if (rotated && lane == 0 && role == 0) atomicAdd(a.sync + 2 + sw, 1u);
-    grid_sync(a.sync, target);
-    sweeps = sw + 1;
-    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
-  }
-  const int gw = blockIdx.x * 4 + warp;
-  const int GW = gridDim.x * 4;
-  // sigma_i^2 = |R part of row i|^2
-  for (int i = gw; i < q; i += GW) {
-    const double* ri = a.Y + (size_t)i * a.ld;
-    double acc = 0.0;
-    for (int col = 2 * lane; col < a.ndot; col += 64) {
-      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
-      acc += v.x * v.x + v.y * v.y;
-    }
-    acc = warp_sum(acc);
-    if (!(acc > thr)) acc = 0.0;
-    if (lane == 0) __stcg(a.norms + i, acc);
-  }
-  grid_sync(a.sync, target);
-  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
-  grid_sync(a.sync, target);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double err;
-    a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
-    a.info[1] = sweeps;
-    a.info[2] = converged;
-    a.info[3] = q;
-    a.derr[0] = err;
-  }
-}
-
-template <int NC>
-void launch_jq_pair(Ctx* ctx, JqArgs& a, int grid) {
-  void* args[] = {&a};
-  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_pair_kernel<NC>, dim3(grid), dim3(128), args, 0, ctx->stream));
-  ctx->launches++;
-}
 
 // ---- block-cyclic variant: 4-row blocks, several rotation steps per grid barrier ---------------------------------------
 // A round of the row-cyclic kernels costs ~3 us and is pure latency (barrier + L2 round trips), whatever the number of
@@ -978,8 +618,9 @@ __device__ __forceinline__ void store_half(const double2 (&z)[NC], double* row, 
   }
 }
 
-template <int NC, int JB>
-__global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
+template <int NC, int JBT>
+__global__ void __launch_bounds__(64 * JBT) jacobi_qr_block_kernel(JqArgs a) {
+  static_assert(JBT == JB, "the kernel body is written for the global block size");
   extern __shared__ double mbuf[];  // [2][JB][ld]: circulating M rows
   __shared__ double cs_s[JB][8];
   int parity = 0;
@@ -1111,15 +752,15 @@ __global__ void __launch_bounds__(64 * JB) jacobi_qr_block_kernel(JqArgs a) {
   }
 }
 
-template <int NC, int JB>
+template <int NC, int JBT>
 void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
   static bool configured = false;
   if (!configured) {
-    QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC, JBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   void* args[] = {&a};
-  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC, JB>, dim3(grid), dim3(64 * JB), args, smem, ctx->stream));
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC, JBT>, dim3(grid), dim3(64 * JBT), args, smem, ctx->stream));
   ctx->launches++;
 }
 
@@ -1202,18 +843,9 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;
   if (agrid > ctx->sms) agrid = ctx->sms;
   for (int pn = 0; pn < npanels; ++pn) {
-    // the register-resident panel kernel is opt-in (QTT_QR_PANEL=reg): measured 35 / 74 / 128 ms of split time per sweep
-    // (bench sweeps 3 / 4 / 5) against 32 / 69 / 127 ms with the shared-memory panel kernel
-    static const bool reg_panel = getenv("QTT_QR_PANEL") && std::string(getenv("QTT_QR_PANEL")) == "reg";
-    if (reg_panel && p <= 256) {
-      qr_panel_reg_kernel<8, 4><<<1, 256, (256 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
-    } else if (reg_panel && p <= 512) {
-      qr_panel_reg_kernel<16, 4><<<1, 256, (512 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
-    } else if (reg_panel && p <= 1024) {
-      qr_panel_reg_kernel<32, 2><<<1, 256, (1024 + q) * sizeof(double), ctx->stream>>>(SE, q, p, ldp, kmax, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
-    } else {
-      qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
-    }
+    // (a register-resident variant of this kernel -- rows in registers, reflector broadcast through shared memory -- was
+    // measured slower in situ, 35 / 74 / 128 ms of split time per sweep against 32 / 69 / 127 ms, and was removed)
+    qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
     check_launch(ctx, "qr_panel");
     if (p <= 256) qr_apply_kernel<8><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
     else if (p <= 512) qr_apply_kernel<16><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
@@ -1254,37 +886,18 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
   if (grid < 1) grid = 1;
-  static const bool one_warp = getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "onewarp";
   const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
-  static const bool blocked = !(getenv("QTT_JACOBI") && std::string(getenv("QTT_JACOBI")) == "pair");
-  if (!one_warp && blocked && half <= 1024 && kmax >= 16) {
-    // block-cyclic kernel: one CTA per pair of JB-row blocks
-    static const int jb = getenv("QTT_JB") ? atoi(getenv("QTT_JB")) : 4;
-    const int nbk = (((kmax + jb - 1) / jb) + 1) & ~1;
-    int bgrid = nbk / 2;
-    if (bgrid > ctx->sms) bgrid = ctx->sms;
-    const size_t smem = (size_t)2 * jb * ldy * sizeof(double);
-    if (jb == 8 && smem <= 200 * 1024 && half <= 512) {
-      if (half <= 64) launch_jq_block<1, 8>(ctx, a, bgrid, smem);
-      else if (half <= 128) launch_jq_block<2, 8>(ctx, a, bgrid, smem);
-      else if (half <= 256) launch_jq_block<4, 8>(ctx, a, bgrid, smem);
-      else launch_jq_block<8, 8>(ctx, a, bgrid, smem);
-    } else {
-      const int nb4 = (((kmax + 3) / 4) + 1) & ~1;
-      int g4 = nb4 / 2;
-      if (g4 > ctx->sms) g4 = ctx->sms;
-      const size_t smem4 = (size_t)2 * 4 * ldy * sizeof(double);
-      if (half <= 64) launch_jq_block<1, 4>(ctx, a, g4, smem4);
-      else if (half <= 128) launch_jq_block<2, 4>(ctx, a, g4, smem4);
-      else if (half <= 256) launch_jq_block<4, 4>(ctx, a, g4, smem4);
-      else if (half <= 512) launch_jq_block<8, 4>(ctx, a, g4, smem4);
-      else launch_jq_block<16, 4>(ctx, a, g4, smem4);  // chi = 512: rows of 1024 + 1024 doubles
-    }
-  } else if (!one_warp && half <= 512) {
-    if (half <= 64) launch_jq_pair<1>(ctx, a, grid);
-    else if (half <= 128) launch_jq_pair<2>(ctx, a, grid);
-    else if (half <= 256) launch_jq_pair<4>(ctx, a, grid);
-    else launch_jq_pair<8>(ctx, a, grid);
+  if (half <= 1024 && kmax >= 16) {
+    // block-cyclic kernel: one CTA (4 warp pairs) per pair of 4-row blocks
+    const int nb4 = (((kmax + JB - 1) / JB) + 1) & ~1;
+    int g4 = nb4 / 2;
+    if (g4 > ctx->sms) g4 = ctx->sms;
+    const size_t smem4 = (size_t)2 * JB * ldy * sizeof(double);
+    if (half <= 64) launch_jq_block<1, JB>(ctx, a, g4, smem4);
+    else if (half <= 128) launch_jq_block<2, JB>(ctx, a, g4, smem4);
+    else if (half <= 256) launch_jq_block<4, JB>(ctx, a, g4, smem4);
+    else if (half <= 512) launch_jq_block<8, JB>(ctx, a, g4, smem4);
+    else launch_jq_block<16, JB>(ctx, a, g4, smem4);  // chi = 512: rows of 1024 + 1024 doubles
   } else if (ldy <= 128) launch_jq<2>(ctx, a, grid);
   else if (ldy <= 256) launch_jq<4>(ctx, a, grid);
   else if (ldy <= 512) launch_jq<8>(ctx, a, grid);
