@@ -89,7 +89,11 @@ QTT_API void qtt_mpo_free(qtt_mpo* A);
 typedef enum {
   QTT_SOLVER_GMRES = 0,        /* `linsolve`: KrylovKit GMRES on (a0 + a1 P) phi = proj(b) */
   QTT_SOLVER_LANCZOS = 1,      /* Krylov variant of `dmrg_target` (reference src/dmrg_target.jl:14-21): Ritz value nearest target */
-  QTT_SOLVER_SHIFT_INVERT = 2  /* `eigsolve_target` (reference src/eigsolve_target.jl:2-9): eigsolve(x -> linsolve(P, x, x, -target)) */
+  QTT_SOLVER_SHIFT_INVERT = 2, /* `eigsolve_target` (reference src/eigsolve_target.jl:2-9): eigsolve(x -> linsolve(P, x, x, -target)) */
+  QTT_SOLVER_DENSE_QR = 3,     /* `linsolve_pseudoinverse` (reference src/linsolve.jl:54-97): dense (4 chi^2)^2 operator, `qr!(T) \ b`;
+                                  solves (a0 + a1 T) x = b -- pass a0 = 0, a1 = 1 for the reference's behaviour (it ignores them) */
+  QTT_SOLVER_DENSE_EIGEN = 4   /* `dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense Hermitian effective operator,
+                                  eigenvector of the eigenvalue nearest `target`.  Dense kinds need 4 chi_l chi_r <= 8192. */
 } qtt_solver_kind;
 
 typedef struct {
@@ -125,11 +129,14 @@ typedef struct {
 
 /* `linsolve(A::MPO, b::MPS, x0::MPS, a0, a1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter)`
  * (reference call sites examples/airy_equation/airy_equation.jl:429, src/eigsolve_target.jl:4;
- * body examples/airy_equation/src/linsolve.jl:24-34).  x is updated in place.  per_sweep: nsweeps entries or NULL. */
+ * body examples/airy_equation/src/linsolve.jl:24-34).  x is updated in place.  per_sweep: nsweeps entries or NULL.
+ * p->solver = QTT_SOLVER_DENSE_QR selects the dense local solve of `linsolve_pseudoinverse` (src/linsolve.jl:54-97);
+ * any other value means GMRES. */
 QTT_API int qtt_linsolve(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* b, qtt_mps* x_inout, const qtt_sweep_params* p, qtt_sweep_info* per_sweep);
 /* `dmrg_target(A, psi0; target_eigenvalue, nsweeps, maxdim, cutoff)` (reference src/dmrg_target.jl:1-12)
  * with the Krylov local solvers the reference sketches at :14-21: p->solver = QTT_SOLVER_LANCZOS (Ritz value nearest target) or
- * QTT_SOLVER_SHIFT_INVERT (`eigsolve_target`, src/eigsolve_target.jl:2-9; fixed_matvecs must be 0). */
+ * QTT_SOLVER_SHIFT_INVERT (`eigsolve_target`, src/eigsolve_target.jl:2-9; fixed_matvecs must be 0), or
+ * QTT_SOLVER_DENSE_EIGEN (the dense `eigen` of :3-7 itself, small bonds only). */
 QTT_API int qtt_dmrg_target(qtt_ctx* ctx, const qtt_mpo* A, qtt_mps* psi_inout, const qtt_sweep_params* p, qtt_sweep_info* per_sweep);
 /* enable per-phase CUDA-event timing inside the sweeps (adds one event pair per phase per bond) */
 QTT_API int qtt_set_profiling(qtt_ctx* ctx, int enabled);

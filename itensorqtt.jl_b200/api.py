@@ -10,11 +10,11 @@ import numpy as np
 from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
 from .chains import DeviceMPS, DeviceMPO
 
-__all__ = ["linsolve", "dmrg_target", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
-           "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT"]
+           "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN"]
 
-SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT = 0, 1, 2
+SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT, SOLVER_DENSE_QR, SOLVER_DENSE_EIGEN = 0, 1, 2, 3, 4
 
 
 def _per_sweep(v, nsweeps, ctype, default):
@@ -63,7 +63,7 @@ def _params(nsweeps, maxdim, mindim, cutoff, solver, a0, a1, tol, krylovdim, max
 
 def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,
              maxiter=10, ishermitian=False, normalize=False, outputlevel=0, fixed_matvecs=None, x0_canonical=False,
-             ctx=None, return_info=False, on_device=False, host_order="C"):
+             ctx=None, return_info=False, on_device=False, host_order="C", _solver=SOLVER_GMRES):
     """`linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter, ishermitian)`
     -- solves (a0 + a1 A) x = b by two-site sweeps with a local GMRES
     (reference examples/airy_equation/src/linsolve.jl:24-34; call sites airy_equation.jl:429, src/eigsolve_target.jl:4).
@@ -73,7 +73,7 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
     dA, fa = _as_dev_mpo(A, ctx)
     db, fb = _as_dev_mps(b, ctx)
     dx = x0.clone() if isinstance(x0, DeviceMPS) else DeviceMPS(x0, ctx)
-    p, keep = _params(nsweeps, maxdim, mindim, cutoff, SOLVER_GMRES, a0, a1, tol, krylovdim, maxiter, fixed_matvecs,
+    p, keep = _params(nsweeps, maxdim, mindim, cutoff, _solver, a0, a1, tol, krylovdim, maxiter, fixed_matvecs,
                       normalize, outputlevel, 0.0, x0_canonical)
     infos = (SweepInfo * max(p.nsweeps, 1))()
     try:
@@ -91,6 +91,17 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
     return out
 
 
+def linsolve_pseudoinverse(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,
+                           maxiter=10, ishermitian=False, **kwargs):
+    """`linsolve_pseudoinverse(A, b, x0, a0=0, a1=1; kwargs...)` (reference src/linsolve.jl:54-97): the same two-site sweep
+    with a DENSE local solve -- the projected operator as a (4 chi_l chi_r)^2 matrix, `qr!(T_mat) \\ b_vec` (:88-89).
+    As in the reference, `a0`, `a1` and the Krylov keywords are accepted and IGNORED (the body never uses them, :67-92):
+    the local problem is T x = b.  Memory grows as chi^4 (reference's own warning, :50-52); the device path accepts
+    4 chi_l chi_r <= 8192 and raises otherwise."""
+    return linsolve(A, b, x0, 0.0, 1.0, nsweeps=nsweeps, maxdim=maxdim, mindim=mindim, cutoff=cutoff, _solver=SOLVER_DENSE_QR,
+                    **kwargs)
+
+
 def dmrg_target(A, psi0, *, target_eigenvalue, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-12, krylovdim=30,
                 maxiter=1, normalize=True, outputlevel=0, fixed_matvecs=None, x0_canonical=False, ctx=None,
                 return_info=False, on_device=False, local_solver="lanczos"):
@@ -98,8 +109,9 @@ def dmrg_target(A, psi0, *, target_eigenvalue, nsweeps=None, maxdim=None, mindim
     the Krylov local solver the reference sketches at :14-21 (dense `eigen` of the (4 chi^2)^2 effective operator is
     infeasible beyond chi ~ 64).  local_solver="lanczos": restarted Lanczos, Ritz value nearest `target_eigenvalue` (extremal
     targets); local_solver="shift_invert": `eigsolve_target` (reference src/eigsolve_target.jl:2-9) =
-    eigsolve(x -> linsolve(P, x, x, -target)), which also resolves interior eigenvalues."""
-    solver = {"lanczos": SOLVER_LANCZOS, "shift_invert": SOLVER_SHIFT_INVERT}[local_solver]
+    eigsolve(x -> linsolve(P, x, x, -target)), which also resolves interior eigenvalues; local_solver="dense": the reference
+    body itself (:3-7) -- dense effective operator, eigenvector of the eigenvalue nearest the target (4 chi_l chi_r <= 8192)."""
+    solver = {"lanczos": SOLVER_LANCZOS, "shift_invert": SOLVER_SHIFT_INVERT, "dense": SOLVER_DENSE_EIGEN}[local_solver]
     ctx = ctx or default_context()
     dA, fa = _as_dev_mpo(A, ctx)
     dx = psi0.clone() if isinstance(psi0, DeviceMPS) else DeviceMPS(psi0, ctx)

@@ -75,6 +75,7 @@ struct Ctx {
   Arena arena;
   std::string err;
   int64_t launches = 0;
+  unsigned dense_epoch = 0;  // value of the dense-QR panel barrier counter (d_sync + 240)
   unsigned bar_epoch = 0;  // value of the fused-Krylov barrier counter (d_sync + 4) after the launches so far
   bool profiling = false;
   // small device scratch for scalars / flags / partial reductions
@@ -183,6 +184,18 @@ void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out /* device sca
 void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out,
                   const double* done_dev = nullptr);
 void kry_axpby(Ctx* ctx, size_t len, double a, const double* x, double b, const double* y, double c, const double* z, double* out);
+
+// ------------------------------------------------------------------ dense local solvers (dense_solve.cu)
+constexpr int DENSE_LEN_MAX = 8192;  // (4 chi_l chi_r) of the largest dense local problem (matrix 8192^2 = 512 MiB)
+bool dense_local_ok(size_t len);
+size_t dense_scratch(size_t len);  // doubles
+// x = (a0 + a1 T)^{-1} beff by Householder QR (reference src/linsolve.jl:88-89); stats_dev[0..3] = (0, 0, zero pivots, max |R_ii|)
+void dense_local_solve(Ctx* ctx, const double* L, const double* W12, const double* R, int chil, int chir, int wl, int wr, double a0,
+                       double a1, const double* beff, double* x, double* scratch, double* stats_dev);
+// x <- eigenvector of T whose eigenvalue is nearest `target` (reference src/dmrg_target.jl:3-7), unit norm;
+// stats_dev[0..3] = (inverse-iteration steps, 1 - |<z_k, z_{k-1}>|, guarded pivots, max |R_ii|)
+void dense_local_eigen(Ctx* ctx, const double* L, const double* W12, const double* R, int chil, int chir, int wl, int wr, double target,
+                       double* x_inout, double* scratch, int maxit, double* stats_dev);
 
 // ------------------------------------------------------------------ SVD split (svd_jacobi.cu)
 struct SplitResult {

@@ -764,14 +764,18 @@ void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
   ctx->launches++;
 }
 
-// Wn[i][:] = carried (Q^T) part of row perm[i]; rows beyond the numerical rank are zero
+// Wn[i][:] = carried (Q^T) part of row perm[i].  Positions beyond the numerical rank r (sigma = 0, kept only because of
+// `mindim`) receive the orthonormal completion LAPACK's SVD would return there: column i of the accumulated Q (the identity
+// block of SE), which is orthogonal to the first r columns.  A zero row instead would make the next bond's projected
+// operator exactly singular.
 __global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
-                                   const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out) {
+                                   const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out,
+                                   const double* __restrict__ SE, int q, int ldp) {
   const int i = blockIdx.y;
   if (i >= k) return;
   const int src = perm[i];
   for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x)
-    Wn[(size_t)i * p + col] = src >= 0 ? Y[(size_t)src * ld + off + col] : 0.0;
+    Wn[(size_t)i * p + col] = src >= 0 ? Y[(size_t)src * ld + off + col] : SE[(size_t)(q + col) * ldp + i];
   if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = sqrt(sig2[i]);
 }
 
@@ -936,7 +940,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   res.Wn = ctx->arena.alloc((size_t)res.k * p);
   res.Wni = nullptr;
   dim3 grid2((p + 255) / 256, res.k);
-  gather_rows_kernel<<<grid2, 256, 0, ctx->stream>>>(Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out);
+  gather_rows_kernel<<<grid2, 256, 0, ctx->stream>>>(Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out, SE, q, ldp);
   check_launch(ctx, "gather_rows");
   return res;
 }

@@ -408,12 +408,15 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   QTT_REQUIRE(A.w[0] == 1 && A.w[n] == 1 && x.chi[0] == 1 && x.chi[n] == 1, "boundary bond dimensions must be 1");
   if (b) QTT_REQUIRE(b->n == n && b->chi[0] == 1 && b->chi[n] == 1, "rhs MPS shape mismatch");
   QTT_REQUIRE(P.nsweeps >= 0, "nsweeps < 0");
-  const bool fixed = P.fixed_matvecs > 0;
-  const int kd = fixed ? P.fixed_matvecs : P.krylovdim;
+  const bool dense_qr = (P.solver == QTT_SOLVER_DENSE_QR), dense_eig = (P.solver == QTT_SOLVER_DENSE_EIGEN);
+  const bool dense = dense_qr || dense_eig;
+  const bool fixed = !dense && P.fixed_matvecs > 0;
+  const int kd = dense ? 1 : (fixed ? P.fixed_matvecs : P.krylovdim);
   QTT_REQUIRE(kd >= 1 && kd <= KD_MAX, "krylovdim must be in [1, %d]", KD_MAX);
   const int maxiter = P.maxiter > 0 ? P.maxiter : 1;
-  const bool is_lin = (P.solver == QTT_SOLVER_GMRES);
-  QTT_REQUIRE(is_lin || P.solver == QTT_SOLVER_LANCZOS || P.solver == QTT_SOLVER_SHIFT_INVERT, "unknown solver kind %d", P.solver);
+  const bool is_lin = (P.solver == QTT_SOLVER_GMRES) || dense_qr;
+  QTT_REQUIRE(is_lin || dense_eig || P.solver == QTT_SOLVER_LANCZOS || P.solver == QTT_SOLVER_SHIFT_INVERT, "unknown solver kind %d",
+              P.solver);
   const bool shift_invert = (P.solver == QTT_SOLVER_SHIFT_INVERT);
   QTT_REQUIRE(!(shift_invert && fixed), "fixed_matvecs is not defined for the shift-invert solver");
   QTT_REQUIRE(!is_lin || b, "linsolve needs a right-hand side");
@@ -492,6 +495,11 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const size_t len = (size_t)4 * chil * chir;
           size_t need = (len * (size_t)(2 * (kd + 1) + 16) + matvec2_scratch(chil, chir, wl, wr) + (size_t)16 * wl * wr + 65536) * sizeof(double);
           need += (size_t)256 * (kd + 24);
+          if (dense) {
+            QTT_REQUIRE(dense_local_ok(len), "dense local solver: 4 chi_l chi_r = %zu exceeds the cap (%d, QTT_DENSE_LEN_MAX) at bond %d; use a Krylov solver",
+                        len, DENSE_LEN_MAX, j);
+            need += (dense_scratch(len) + 64) * sizeof(double);
+          }
           ctx->ensure_arena(need);
           size_t mark = ctx->arena.mark();
           double* phi = ctx->arena.alloc(len);
@@ -512,7 +520,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const double* Rp = RA[j + 2].p;
           MatvecFn mv = [&](const double* in, double* out) { matvec2(ctx, Lp, W12, Rp, in, out, chil, chir, wl, wr, mvscr); };
           LocalStats st;
-          bool small_pending = false;
+          bool small_pending = false, dense_pending = false;
           const double tk0 = info.t_krylov, ts0 = info.t_svd, te0 = info.t_env;
           const int kdl = (size_t)kd < len ? kd : (int)len;  // a Krylov space cannot exceed the local dimension
           {
@@ -521,7 +529,17 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               double* beff = ctx->arena.alloc(len);
               project_rhs(ctx, LB[j].p, b->core[j].p, b->core[j + 1].p, RB[j + 2].p, beff, chil, chir, (int)b->chi[j], (int)b->chi[j + 1],
                           (int)b->chi[j + 2]);
-              if (gmres_small_ok(chil, chir, wl, wr, kdl)) {
+              if (dense_qr) {
+                // `linsolve_pseudoinverse` (reference src/linsolve.jl:67-92): dense operator, Householder QR, back substitution;
+                // the true residual |b - (a0 + a1 P) x| is measured with one matvec for `solver_resid`
+                double* dscr = ctx->arena.alloc(dense_scratch(len));
+                dense_local_solve(ctx, Lp, W12, Rp, chil, chir, wl, wr, P.a0, P.a1, beff, phi, dscr, ctx->d_scal + 8);
+                mv(phi, ws.w);
+                kry_axpby(ctx, len, 1.0, beff, -P.a0, phi, -P.a1, ws.w, ws.r);
+                kry_nrm2sq(ctx, ws.r, len, ctx->d_scal + 12);
+                QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 72, ctx->d_scal + 8, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                dense_pending = true;
+              } else if (gmres_small_ok(chil, chir, wl, wr, kdl)) {
                 // whole local solve in one single-CTA kernel (krylov_small.cu); statistics are read after the split's sync
                 gmres_small(ctx, Lp, W12, Rp, beff, phi, chil, chir, wl, wr, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws.V, ctx->d_scal + 8);
                 QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 72, ctx->d_scal + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,6 +547,15 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               } else {
                 gmres_local(ctx, mv, beff, phi, len, P.a0, P.a1, P.tol, kdl, maxiter, fixed, ws, st);
               }
+            } else if (dense_eig) {
+              // `dmrg_target` as written (reference src/dmrg_target.jl:3-7): dense operator, eigenvector nearest the target;
+              // energy = Rayleigh quotient <x, P x> of the returned unit vector
+              double* dscr = ctx->arena.alloc(dense_scratch(len));
+              dense_local_eigen(ctx, Lp, W12, Rp, chil, chir, wl, wr, P.target, phi, dscr, 0, ctx->d_scal + 8);
+              mv(phi, ws.w);
+              kry_dots(ctx, phi, 1, len, ws.w, ctx->d_scal + 12);
+              QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 72, ctx->d_scal + 8, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+              dense_pending = true;
             } else if (shift_invert) {
               // `eigsolve_target` (reference src/eigsolve_target.jl:2-9) as the local solver (src/dmrg_target.jl:14-21):
               // eigsolve(x -> linsolve(P, x, x, -target)), dominant eigenpair of the inverse.  The inner GMRES uses the default
@@ -550,9 +577,9 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               info.energy = st.theta;
             }
           }
-          if (fixed && is_lin && !small_pending)
+          if (fixed && is_lin && !small_pending && !dense_pending)
             QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 70, ctx->d_scal + S_BETA, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-          if (!small_pending) {
+          if (!small_pending && !dense_pending) {
             info.matvecs += st.matvecs;
             info.flops_matvec += (double)st.matvecs * matvec_flops(chil, chir, wl, wm, wr);
             if (st.resid > info.solver_resid) info.solver_resid = st.resid;
@@ -578,7 +605,19 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
             PhaseTimer pt(ctx, &info.t_svd);
             sr = split2(ctx, phi, chil, chir, dir, cutoff, maxdim, mindim, x.core[j].p, x.core[j + 1].p, nullptr, P.svd_max_sweeps);
           }
-          if (small_pending) {  // split2 synchronised the stream: the single-CTA solver's statistics have arrived
+          if (dense_pending) {  // split2 synchronised the stream: the dense solver's statistics have arrived
+            info.matvecs += 1;
+            info.flops_matvec += matvec_flops(chil, chir, wl, wm, wr);
+            if (dense_qr) {
+              if (ctx->h_scal[74] > 0.0)
+                fail(QTT_ERR_NOCONV, "dense QR local solve: exactly singular projected operator at bond %d (zero pivot)", j);
+              const double rr = sqrt(ctx->h_scal[76]);
+              if (rr > info.solver_resid) info.solver_resid = rr;
+            } else {
+              info.energy = ctx->h_scal[76];
+              if (ctx->h_scal[73] > info.solver_resid) info.solver_resid = ctx->h_scal[73];
+            }
+          } else if (small_pending) {  // split2 synchronised the stream: the single-CTA solver's statistics have arrived
             const double mvs = ctx->h_scal[72];
             info.matvecs += (int64_t)mvs;
             info.flops_matvec += mvs * matvec_flops(chil, chir, wl, wm, wr);

@@ -55,6 +55,8 @@ end
 const QTT_SOLVER_GMRES = Int32(0)
 const QTT_SOLVER_LANCZOS = Int32(1)
 const QTT_SOLVER_SHIFT_INVERT = Int32(2)   # `eigsolve_target` (reference src/eigsolve_target.jl:2-9) as the local solver
+const QTT_SOLVER_DENSE_QR = Int32(3)       # `linsolve_pseudoinverse` (reference src/linsolve.jl:54-97): dense operator, qr! \ b
+const QTT_SOLVER_DENSE_EIGEN = Int32(4)    # `dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense Hermitian eigen
 
 struct QttError <: Exception
   code::Int
@@ -192,7 +194,7 @@ by two-site sweeps with a local GMRES, on the GPU.
 """
 function linsolve(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; nsweeps, maxdim=typemax(Int32), mindim=1,
                   cutoff=1e-16, tol=1e-5, krylovdim=20, maxiter=10, ishermitian=false, normalize=false, outputlevel=0,
-                  ctx::Context=context())
+                  ctx::Context=context(), local_solver=QTT_SOLVER_GMRES)
   (a0 isa Real && a1 isa Real) || error("libqtt_b200: complex a0/a1 are not supported by this build")
   hA = upload(ctx, A); hb = upload(ctx, b); hx = upload(ctx, x0)
   md = sweepvec(Int32, min.(maxdim, typemax(Int32)), nsweeps)
@@ -201,7 +203,7 @@ function linsolve(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; nsweeps, 
   infos = Vector{QttSweepInfo}(undef, nsweeps)
   try
     GC.@preserve md mn co begin
-      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), QTT_SOLVER_GMRES, a0, a1, tol, krylovdim, maxiter,
+      p = Ref(QttSweepParams(nsweeps, pointer(md), pointer(mn), pointer(co), local_solver, a0, a1, tol, krylovdim, maxiter,
                              0, normalize, outputlevel, 0.0, 0, 0))
       check(ctx, ccall((:qtt_linsolve, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{QttSweepParams}, Ptr{QttSweepInfo}),
                        ctx.handle, hA, hb, hx, p, infos))
@@ -213,10 +215,22 @@ function linsolve(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; nsweeps, 
 end
 
 """
+    linsolve_pseudoinverse(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, mindim, cutoff, kwargs...)
+
+Reference src/linsolve.jl:54-97: the same sweep with the dense local solve `qr!(T_mat) \\ b_vec` (:88-89) on the GPU
+(blocked Householder QR on the DMMA GEMM core).  As in the reference body, `a0`, `a1` and the Krylov keywords are
+accepted and ignored (:67-92).  Local dimension 4 chi_l chi_r <= 8192; larger bonds raise a QttError.
+"""
+linsolve_pseudoinverse(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; tol=1e-5, krylovdim=20, maxiter=10,
+                       ishermitian=false, reverse_step=false, nsite=2, kwargs...) =
+  linsolve(A, b, x0, 0, 1; local_solver=QTT_SOLVER_DENSE_QR, kwargs...)
+
+"""
     dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim, cutoff, ...)
 
-Reference src/dmrg_target.jl:1-12 with the Krylov local solver sketched at :14-21 (the dense `eigen` of the
-(4 chi^2)^2 effective operator does not exist beyond chi ~ 64).
+Reference src/dmrg_target.jl:1-12.  `local_solver = QTT_SOLVER_DENSE_EIGEN` is the reference body itself (dense
+effective operator, eigenvector of the eigenvalue nearest the target; 4 chi_l chi_r <= 8192); the default is the Krylov
+local solver sketched at :14-21, which scales to chi = 512 where the dense operator would be 8.8 TB.
 """
 function dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim=typemax(Int32), mindim=1, cutoff=1e-16, tol=1e-12,
                      krylovdim=30, maxiter=1, outputlevel=0, local_solver=QTT_SOLVER_LANCZOS, ctx::Context=context())

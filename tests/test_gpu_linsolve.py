@@ -126,3 +126,69 @@ def test_dmrg_target_shift_invert_interior_eigenvalue(lib):
     v /= np.linalg.norm(v)
     assert 1 - abs(v @ U[:, near]) < 1e-8
     assert abs(info[-1]["energy"] - D[near]) < 1e-8 * abs(D[near])
+
+
+@pytest.mark.parametrize("n,chi", [(6, 4), (9, 10), (10, 16)])
+def test_linsolve_pseudoinverse_dense_qr_parity(lib, n, chi):
+    """`linsolve_pseudoinverse` (reference src/linsolve.jl:54-97): dense projected operator + Householder QR on the device
+    vs the oracle's restatement (numpy QR + triangular solve) on the same inputs; bonds up to len = 4 * 10 * 10 = 400
+    exercise several 32-reflector panels."""
+    A, b, Am, bv = _airy(n)
+    x0 = O.random_mps(n, chi, 1234)
+    kw = dict(nsweeps=2, maxdim=chi, cutoff=1e-13)
+    xo, _ = O.linsolve_pseudoinverse(A, b, x0, **kw)
+    xg, info = lib.linsolve_pseudoinverse(A, b, x0, return_info=True, **kw)
+    assert O.fidelity_defect(xo, xg) <= 1e-10
+    vo = O.mps_to_discrete_function(xo); vg = O.mps_to_discrete_function(xg)
+    ro = np.linalg.norm(Am @ vo - bv) / np.linalg.norm(bv)
+    rg = np.linalg.norm(Am @ vg - bv) / np.linalg.norm(bv)
+    assert rg <= 1.05 * ro + 1e-12
+    assert info[-1]["matvecs"] == 2 * (n - 1)          # one residual-check matvec per bond, none for the solve
+    # a0 / a1 are accepted and ignored, as in the reference body (:67-92)
+    xs = lib.linsolve_pseudoinverse(A, b, x0, 0.5, 2.0, **kw)
+    assert O.fidelity_defect(xg, xs) <= 1e-13
+
+
+def test_dense_qr_local_solver_honours_shift_at_the_c_abi(lib):
+    """At the C ABI QTT_SOLVER_DENSE_QR solves (a0 + a1 T) x = b (the Python/Julia mirrors pin a0 = 0, a1 = 1): same answer as
+    converged GMRES on the shifted Helmholtz problem."""
+    n = 8
+    Al = O.laplacian_mpo(n, 1.0)
+    lam = O.helmholtz_lambda(n, 2)
+    b = O.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
+    x0 = O.random_mps(n, 6, 2)
+    kw = dict(nsweeps=2, maxdim=8, cutoff=1e-13)
+    xk = lib.linsolve(Al, b, x0, -lam, 1.0, tol=1e-13, krylovdim=30, maxiter=20, **kw)
+    xd = lib.linsolve(Al, b, x0, -lam, 1.0, _solver=lib.SOLVER_DENSE_QR, **kw)
+    assert O.fidelity_defect(xk, xd) <= 1e-10
+
+
+def test_dmrg_target_dense_eigen_parity(lib):
+    """`dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense effective operator, eigenvector nearest the target.
+    Interior target (Helmholtz mode nk = 2) -> same state as the oracle's `eigh` + argmin, and the known eigenpair."""
+    n = 7
+    Al = O.laplacian_mpo(n, 1.0)
+    Lm = O.laplacian_matrix(2 ** n)
+    D, U = np.linalg.eigh(Lm)
+    target = O.helmholtz_lambda(n, 2) * 1.001
+    near = int(np.argmin(np.abs(D - target)))
+    psi0 = O.vec_to_mps(U[:, near] + 0.3 * np.random.default_rng(0).standard_normal(2 ** n), cutoff=1e-12, maxdim=6)
+    kw = dict(nsweeps=2, maxdim=8, cutoff=1e-13)
+    po, _ = O.dmrg_target(Al, psi0, target, normalize=True, **kw)
+    pg, info = lib.dmrg_target(Al, psi0, target_eigenvalue=target, return_info=True, local_solver="dense", **kw)
+    assert O.fidelity_defect(po, pg) <= 1e-10
+    v = O.mps_to_discrete_function(pg)
+    v /= np.linalg.norm(v)
+    assert 1 - abs(v @ U[:, near]) < 1e-9
+    assert abs(info[-1]["energy"] - D[near]) < 1e-10 * abs(D[near])
+
+
+def test_dense_solver_refuses_large_bonds(lib, monkeypatch):
+    """The dense modes are chi^4 in memory (reference's own warning, src/linsolve.jl:50-52): beyond the cap the call fails
+    loudly instead of falling back to anything."""
+    n = 9
+    A, b, _, _ = _airy(n)
+    x0 = O.random_mps(n, 10, 3)                          # interior bonds: 4 * 10 * 10 = 400
+    monkeypatch.setenv("QTT_DENSE_LEN_MAX", "256")
+    with pytest.raises(Exception, match="dense local solver"):
+        lib.linsolve_pseudoinverse(A, b, x0, nsweeps=1, maxdim=10, mindim=10, cutoff=0.0)
