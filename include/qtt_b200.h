@@ -147,6 +147,17 @@ QTT_API int qtt_set_profiling(qtt_ctx* ctx, int enabled);
  * site index; chain reversal / output-bit relabelling stay in the caller (src/dft.jl:76-79,124). */
 QTT_API int qtt_apply(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* psi, double cutoff, int32_t maxdim, int32_t mindim, qtt_mps** out);
 
+/* ---- TT-SVD of a sampled function ------------------------------------------------------------
+ * `vec_to_mps(v, s; cutoff, maxdim, mindim)` = `MPS(vec_to_tensor(v), s; ...)` (reference src/function_to_mps.jl:170-177):
+ * the back end of `function_to_mps(f, s, xstart, xstop; alg="factorize", cutoff=1e-15)` (:41-52) once f is sampled on
+ * `qtt_xrange` (:10-12).  v: 2^n doubles, v[j] = f(x_j), site 1 = most significant bit of j; host memory
+ * (on_device = 0: uploaded once) or device memory on ctx's GPU (on_device = 1: read in place, not modified).
+ * Left-to-right sweep of truncated SVDs with the NDTensors.truncate! rule (relative cutoff on the discarded weight);
+ * the result is left-orthogonal with its orthogonality centre at site n, as upstream.  maxdim = 0: unlimited (this build
+ * supports bond dimensions up to 512).  maxtruncerr (may be NULL) receives the largest per-bond discarded weight. */
+QTT_API int qtt_vec_to_mps(qtt_ctx* ctx, const double* v, int32_t n, int32_t on_device, double cutoff, int32_t maxdim, int32_t mindim,
+                           qtt_mps** out, double* maxtruncerr);
+
 /* ---- metrics (reference src/mps_utils.jl:109-132) ------------------------------------------- */
 /* inner(x, y) = <x|y>; out2 = {re, im} */
 QTT_API int qtt_inner(qtt_ctx* ctx, const qtt_mps* x, const qtt_mps* y, double* out2);

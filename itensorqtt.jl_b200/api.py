@@ -10,7 +10,7 @@ import numpy as np
 from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
 from .chains import DeviceMPS, DeviceMPO
 
-__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "vec_to_mps", "function_to_mps", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
            "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN"]
 
@@ -151,6 +151,46 @@ def apply(A, psi, *, cutoff=1e-13, maxdim=None, mindim=1, ctx=None, on_device=Fa
     cores = res.download()
     res.free()
     return cores
+
+
+def vec_to_mps(v, *, cutoff=1e-15, maxdim=None, mindim=1, ctx=None, on_device=False, return_info=False):
+    """`vec_to_mps(v, s; cutoff, maxdim, mindim)` = `MPS(vec_to_tensor(v), s; ...)` (reference src/function_to_mps.jl:170-177):
+    TT-SVD of 2^n samples on the GPU, site 1 = most significant bit, orthogonality centre at site n.
+    v: host array of length 2^n, or a CUDA tensor / object with `data_ptr()` and `numel()` already on the context's device
+    (read in place)."""
+    ctx = ctx or default_context()
+    if hasattr(v, "data_ptr"):
+        total = int(v.numel())
+        ptr, dev = C.c_void_p(int(v.data_ptr())), 1
+        hold = v
+    else:
+        hold = np.ascontiguousarray(np.asarray(v), dtype=np.float64).reshape(-1)
+        if np.iscomplexobj(v):
+            raise NotImplementedError("vec_to_mps: complex samples are not supported by this build")
+        total = hold.size
+        ptr, dev = C.c_void_p(hold.ctypes.data), 0
+    n = int(total).bit_length() - 1
+    if total < 2 or (1 << n) != total:
+        raise ValueError(f"vec_to_mps: length {total} is not a power of two >= 2")
+    out = C.c_void_p()
+    err = C.c_double(0.0)
+    check(ctx.handle, lib.qtt_vec_to_mps(ctx.handle, ptr, n, dev, float(cutoff), int(maxdim or 0), int(mindim), C.byref(out), C.byref(err)))
+    del hold
+    res = DeviceMPS(ctx=ctx, _handle=out)
+    if not on_device:
+        cores = res.download()
+        res.free()
+        res = cores
+    return (res, {"maxtruncerr": err.value}) if return_info else res
+
+
+def function_to_mps(f, n, xstart, xstop, *, cutoff=1e-15, alg="factorize", **kwargs):
+    """`function_to_mps(f, s, xstart, xstop; alg="factorize", cutoff=1e-15)` (reference src/function_to_mps.jl:22-52): sample
+    f on `qtt_xrange(n, xstart, xstop)` (vectorised numpy callable) and TT-SVD the samples on the GPU."""
+    if alg != "factorize":
+        raise NotImplementedError('only alg="factorize" runs on the device; the polynomial construction (:88-133) is host-side')
+    from .operators import qtt_xrange
+    return vec_to_mps(f(qtt_xrange(n, xstart, xstop)), cutoff=cutoff, **kwargs)
 
 
 def inner(x, y, ctx=None):

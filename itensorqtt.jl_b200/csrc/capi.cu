@@ -458,6 +458,33 @@ int qtt_apply(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* psi, double cutoff,
   QTT_CATCH(ctx)
 }
 
+int qtt_vec_to_mps(qtt_ctx* ctx, const double* v, int32_t n, int32_t on_device, double cutoff, int32_t maxdim, int32_t mindim, qtt_mps** out,
+                   double* maxtruncerr) {
+  QTT_TRY(ctx)
+  QTT_REQUIRE(ctx && v && out, "qtt_vec_to_mps: null argument");
+  QTT_REQUIRE(n >= 1 && n <= 34, "qtt_vec_to_mps: n = %d out of range [1, 34]", n);
+  QTT_CUDA(cudaSetDevice(ctx->device));
+  const size_t total = (size_t)1 << n;
+  double* staged = nullptr;
+  if (!on_device) {
+    staged = static_cast<double*>(pool_alloc(total * sizeof(double), ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(staged, v, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { pool_free(staged, ctx->stream); QTT_CUDA(e); }
+  }
+  qtt_mps* m = new qtt_mps();
+  try {
+    vec_to_mps(ctx, staged ? staged : v, n, cutoff, maxdim, mindim, *m, maxtruncerr);
+  } catch (...) {
+    delete m;
+    if (staged) pool_free(staged, ctx->stream);
+    throw;
+  }
+  if (staged) pool_free(staged, ctx->stream);
+  if (total >= ((size_t)1 << 26)) pool_trim();  // do not keep multi-GB staging buffers cached
+  *out = m;
+  QTT_CATCH(ctx)
+}
+
 int qtt_inner(qtt_ctx* ctx, const qtt_mps* x, const qtt_mps* y, double* out2) {
   QTT_TRY(ctx)
   QTT_REQUIRE(ctx && x && y && out2, "qtt_inner: null argument");

@@ -224,6 +224,9 @@ RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxd
 SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, double cutoff, int maxdim, int mindim,
                    double* A_out, double* B_out, double* sigma_out /* device, may be null */, int max_sweeps);
 
+// ------------------------------------------------------------------ TT-SVD of a sample vector (ttsvd.cu)
+void vec_to_mps(Ctx* ctx, const double* v_dev, int n, double cutoff, int maxdim, int mindim, Mps& out, double* maxerr_out);
+
 }  // namespace qtt
 
 struct qtt_ctx : qtt::Ctx {};

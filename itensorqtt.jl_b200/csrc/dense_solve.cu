@@ -416,7 +416,7 @@ void dense_qr_rows(Ctx* ctx, double* base, const DenseLayout& d, int n, int nrow
 void launch_tri(Ctx* ctx, TriArgs& a) {
   const size_t smem = sizeof(double) * (size_t)a.n * (a.eigen ? 2 : 1);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 10 * 1024 > 48 * 1024 && smem > configured) {  // static shared memory (8.7 KB) counts against the 48 KB default
     QTT_CUDA(cudaFuncSetAttribute(dtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     configured = 200 * 1024;
   }

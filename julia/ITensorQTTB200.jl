@@ -293,6 +293,35 @@ function apply_idft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
 end
 
 # residual metric of reference src/mps_utils.jl:109-116
+"""
+    vec_to_mps(v::AbstractVector, s::Vector{<:Index}; cutoff=1e-15, maxdim=0, mindim=1)
+    function_to_mps(f, s, xstart, xstop; cutoff=1e-15, kwargs...)     # alg = "factorize"
+
+Reference src/function_to_mps.jl:41-52,170-177 (`MPS(vec_to_tensor(v), s; cutoff)`): the TT-SVD runs on the GPU
+(streaming Gram + orthogonal projection per site); a 2^30-sample vector takes ~0.2 s of device time on one B200.
+The Julia vector is already in the order the C ABI wants (index j-1 = sum_k b_k 2^(n-k), site 1 = MSB), no permute.
+"""
+function vec_to_mps(v::AbstractVector{<:Real}, s::Vector{<:Index}; cutoff=1e-15, maxdim=0, mindim=1, ctx::Context=context())
+  n = length(s)
+  length(v) == 2^n || error("vec_to_mps: length(v) must be 2^length(s)")
+  vv = convert(Vector{Float64}, v)
+  out = Ref{Ptr{Cvoid}}(C_NULL); err = Ref{Cdouble}(0.0)
+  try
+    check(ctx, ccall((:qtt_vec_to_mps, libqtt), Cint,
+                     (Ptr{Cvoid}, Ptr{Cdouble}, Int32, Int32, Cdouble, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Cdouble}),
+                     ctx.handle, vv, n, 0, cutoff, min(maxdim, typemax(Int32)), mindim, out, err))
+    return download(ctx, out[], s)
+  finally
+    out[] != C_NULL && free_mps(out[])
+  end
+end
+
+function function_to_mps(f::Function, s::Vector{<:Index}, xstart, xstop; cutoff=1e-15, kwargs...)
+  n = length(s)
+  x = range(; start=xstart, stop=xstop, length=(2^n + 1))[1:(2^n)]   # qtt_xrange, src/function_to_mps.jl:10-12
+  return vec_to_mps(f.(x), s; cutoff, kwargs...)
+end
+
 function sqeuclidean_normalized(A::MPO, x::MPS, b::MPS; ctx::Context=context())
   hA = upload(ctx, A); hx = upload(ctx, x); hb = upload(ctx, b)
   sq = Ref{Float64}(0.0); sqn = Ref{Float64}(0.0)
