@@ -10,7 +10,8 @@ import numpy as np
 from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
 from .chains import DeviceMPS, DeviceMPO
 
-__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "vec_to_mps", "function_to_mps", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "vec_to_mps", "function_to_mps", "apply_dft_mpo", "apply_idft_mpo",
+           "fourier_interpolation", "repeat_function", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
            "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN"]
 
@@ -364,6 +365,66 @@ def retract(psi, nretract=1, *, cutoff=1e-8, maxdim=None, ctx=None):
         cores = [c.copy() for c in out[:-1]]
         cores[0] = 0.5 * cores[0]
     return cores
+
+
+def apply_dft_mpo(psi, *, cutoff=1e-13, maxdim=None, ctx=None):
+    """`apply_dft_mpo(psi; kwargs...)` = reverse(apply(dft_mpo(s), psi; kwargs...)) (reference src/dft.jl:121-126): site 1 of the
+    result is the most significant bit of the frequency index.  The MPO.MPS apply runs on the GPU (ComplexF64, planar);
+    the DFT MPO comes from the host cache (`operators.dft_mpo`)."""
+    from .operators import dft_mpo
+    cores = [np.asarray(c, dtype=np.complex128) for c in _host_cores(psi)]
+    out = apply(dft_mpo(len(cores)), cores, cutoff=cutoff, maxdim=maxdim, ctx=ctx)
+    return [np.ascontiguousarray(np.transpose(c, (2, 1, 0))) for c in reversed(out)]
+
+
+def apply_idft_mpo(psi, *, cutoff=1e-13, maxdim=None, ctx=None):
+    """`apply_idft_mpo(psi; kwargs...)` = apply(idft_mpo(s), reverse(psi); kwargs...) (reference src/dft.jl:128-133)."""
+    from .operators import idft_mpo
+    cores = [np.asarray(c, dtype=np.complex128) for c in _host_cores(psi)]
+    rpsi = [np.ascontiguousarray(np.transpose(c, (2, 1, 0))) for c in reversed(cores)]
+    return apply(idft_mpo(len(cores)), rpsi, cutoff=cutoff, maxdim=maxdim, ctx=ctx)
+
+
+def _basis_site(bit):
+    c = np.zeros((1, 2, 1), dtype=np.complex128)
+    c[0, bit, 0] = 1.0
+    return c
+
+
+def fourier_interpolation(psi, k=1, *, cutoff=1e-15, ctx=None):
+    """`fourier_interpolation(psi, k; cutoff=1e-15)` (reference src/fourier_interpolation.jl:1-19, arXiv:1909.06619): QTT of length n
+    -> length n + k.  Both transforms (the O(n w^2 chi^3) work) run on the GPU.  The step between them --
+    `project_bits(F, [0])`, `project_bits(F, [1])`, k + 1 basis sites in front of each, `+(...; cutoff=1e-15)` (:4-8) -- is
+    written out exactly: the two summands share every core after the frequency MSB, so their sum is the chain whose first
+    k + 1 sites are the copy tensor delta(l, s, r) on a bond of 2 and whose next core stacks the two projected cores; the
+    inverse-DFT `apply` truncates with `cutoff` exactly as it does after the reference's compression of that sum."""
+    F = apply_dft_mpo(psi, cutoff=cutoff, ctx=ctx)
+    n = len(F)
+    if n < 2:
+        raise ValueError("fourier_interpolation needs at least 2 sites")
+    head = []
+    for i in range(k + 1):
+        l, r = (1 if i == 0 else 2), 2
+        c = np.zeros((l, 2, r), dtype=np.complex128)
+        for b in range(2):
+            c[b if l == 2 else 0, b, b] = 1.0
+        head.append(c)
+    # bond value b selects the projection of the frequency MSB: row b of the stacked core = F[0][0, b, :] . F[1]
+    nxt = np.stack([np.tensordot(F[0][0, b, :], F[1], axes=([0], [0])) for b in range(2)], axis=0)
+    Fi = head + [nxt] + [c for c in F[2:]]
+    out = apply_idft_mpo(Fi, cutoff=cutoff, ctx=ctx)
+    out[0] = out[0] * 2.0 ** (k / 2)
+    return out
+
+
+def repeat_function(psi, k=1, *, cutoff=1e-15, ctx=None):
+    """`repeat_function(psi, k; cutoff=1e-15)` (reference src/fourier_interpolation.jl:21-38): repeat the function 2^k times =
+    DFT, k |0> sites appended as the low frequency bits, inverse DFT, times 2^(k/2).  Both transforms on the GPU."""
+    F = apply_dft_mpo(psi, cutoff=cutoff, ctx=ctx)
+    Fk = F + [_basis_site(0) for _ in range(k)]
+    out = apply_idft_mpo(Fk, cutoff=cutoff, ctx=ctx)
+    out[0] = out[0] * 2.0 ** (k / 2)
+    return out
 
 
 def multigrid_linsolve(problem, levels, x0, a0=0, a1=1, *, prolong_cutoff=1e-15, ctx=None, return_history=False, **kw):

@@ -7,7 +7,7 @@ import numpy as np
 
 __all__ = ["qtt_xrange", "laplacian_mpo", "boundary_value_mps", "prolongation_mpo", "retraction_mpo", "shift_mpo",
            "helmholtz_lambda", "index_to_bits", "bits_to_index", "project_bits", "mps_to_discrete_function",
-           "random_mps", "qtt_exp", "qtt_sin", "qtt_cos", "mps_add_directsum"]
+           "random_mps", "qtt_exp", "qtt_sin", "qtt_cos", "mps_add_directsum", "dft_mpo", "idft_mpo"]
 
 
 def qtt_xrange(n, xstart, xstop):
@@ -186,3 +186,84 @@ def qtt_sin(alpha, n, beta=0.0):
 def qtt_cos(alpha, n, beta=0.0):
     """reference src/qtt_utils.jl:67-76."""
     return _scale(mps_add_directsum(qtt_exp(1j * alpha, beta, n), qtt_exp(-1j * alpha, beta, n)), 0.5)
+
+
+# ------------------------------------------------------------------ DFT operator (reference src/dft.jl)
+def _truncate_rule(p, cutoff, maxdim=None):
+    """NDTensors.truncate! on descending weights p: drop from the tail while the dropped weight <= cutoff * sum(p)."""
+    n = len(p)
+    if maxdim is not None:
+        n = min(n, int(maxdim))
+    err = float(np.sum(p[n:]))
+    scale = float(np.sum(p)) or 1.0
+    while n > 1 and err + p[n - 1] <= cutoff * scale:
+        err += p[n - 1]
+        n -= 1
+    return n
+
+
+def _mpo_compress(M, cutoff):
+    """Canonical compression of a small MPO [l, r, s, t]: QR sweep to the right end, truncated-SVD sweep back."""
+    M = [c.copy() for c in M]
+    n = len(M)
+    for j in range(n - 1):
+        a, c, d1, d2 = M[j].shape
+        Q, R = np.linalg.qr(np.transpose(M[j], (0, 2, 3, 1)).reshape(a * d1 * d2, c))
+        k = Q.shape[1]
+        M[j] = np.transpose(Q.reshape(a, d1, d2, k), (0, 3, 1, 2))
+        M[j + 1] = np.tensordot(R, M[j + 1], axes=([1], [0]))
+    for j in range(n - 1, 0, -1):
+        a, c, d1, d2 = M[j].shape
+        U, S, Vh = np.linalg.svd(np.transpose(M[j], (0, 2, 3, 1)).reshape(a, d1 * d2 * c), full_matrices=False)
+        k = _truncate_rule(S ** 2, cutoff)
+        M[j] = np.transpose(Vh[:k].reshape(k, d1, d2, c), (0, 3, 1, 2))
+        M[j - 1] = np.transpose(np.tensordot(M[j - 1], U[:, :k] * S[None, :k], axes=([1], [0])), (0, 3, 1, 2))
+    return M
+
+
+def _hadamard_phase_layer(n, j):
+    """reference src/dft.jl:51-74,84-93: identity on sites 1..j-1, then delta(s, s', l) with a Hadamard on the output of site
+    j and the controlled phases exp(-i pi / 2^(m-1)) on the m-th site of the block (cores [l, r, s_in, s_out])."""
+    cores = [np.eye(2, dtype=np.complex128).reshape(1, 1, 2, 2) for _ in range(j - 1)]
+    m = n - j + 1
+    H = np.array([[1.0, 1.0], [1.0, -1.0]], dtype=np.complex128) / np.sqrt(2.0)
+    if m == 1:
+        cores.append(H.reshape(1, 1, 2, 2).copy())          # apply(H, I)
+        return cores
+    first = np.zeros((1, 2, 2, 2), dtype=np.complex128)
+    for b in range(2):
+        first[0, b, b, :] = H[:, b]                           # delta(s, s', l) followed by H on the output leg
+    cores.append(first)
+    for i in range(2, m + 1):
+        c = np.zeros((2, 2 if i < m else 1, 2, 2), dtype=np.complex128)
+        c[0, 0] = np.eye(2)
+        c[1, 1 if i < m else 0] = np.diag([1.0, np.exp(-1j * np.pi / 2 ** (i - 1))])
+        cores.append(c)
+    return cores
+
+
+_DFT_CACHE = {}
+
+
+def dft_mpo(n, cutoff=1e-15):
+    """`dft_mpo(s; cutoff=1e-15)` (reference src/dft.jl:81-99, alg="mpo"): the product of the n Hadamard+phase layers,
+    compressed with `cutoff` after every product, then swapprime(0 <-> 1).  Returned BEFORE `reverse_output_bits` (an
+    Index relabelling in the reference, :76-79): output site q of these cores carries frequency bit n+1-q, which is what
+    `apply` sees; `apply_dft_mpo` reverses the chain afterwards (:124).  Tiny (bond <= 11): built on the host once per
+    (n, cutoff) and cached -- the reference rebuilds it on every `apply_dft_mpo` call (:123)."""
+    key = (int(n), float(cutoff))
+    if key not in _DFT_CACHE:
+        U = _hadamard_phase_layer(n, 1)
+        for j in range(2, n + 1):
+            V = _hadamard_phase_layer(n, j)
+            # operator product U o V (input -> V -> U): bonds multiply, then compress
+            prod = [np.einsum("aetu,bfst->abefsu", U[i], V[i]).reshape(U[i].shape[0] * V[i].shape[0], U[i].shape[1] * V[i].shape[1], 2, 2)
+                    for i in range(n)]
+            U = _mpo_compress(prod, cutoff)
+        _DFT_CACHE[key] = [np.ascontiguousarray(np.transpose(c, (0, 1, 3, 2))) for c in U]
+    return [c.copy() for c in _DFT_CACHE[key]]
+
+
+def idft_mpo(n, cutoff=1e-15):
+    """`idft_mpo(s)` = swapprime(dag(dft_mpo(s)), 0 => 1) (reference src/dft.jl:44-46), raw (before bit relabelling)."""
+    return [np.ascontiguousarray(np.transpose(c.conj(), (0, 1, 3, 2))) for c in dft_mpo(n, cutoff)]

@@ -154,3 +154,37 @@ def test_multigrid_linsolve_airy(lib):
     x7 = lib.linsolve(A7, b7, O.random_mps(7, 4, 1), nsweeps=3, maxdim=16, cutoff=1e-13, tol=1e-12, krylovdim=30, maxiter=10)
     guess = dense(lib.prolongate(x7, cutoff=1e-15))
     assert 1 - abs(guess @ xd) / np.linalg.norm(guess) / np.linalg.norm(xd) < 1e-3   # last point interpolates towards 0
+
+
+def test_mirror_dft_front_ends_match_fft(lib):
+    """`apply_dft_mpo` / `apply_idft_mpo` of the host mirror (reference src/dft.jl:121-133) with the cached host-built DFT MPO."""
+    n = 10
+    psi = sines(n)
+    f = dense(psi)
+    Fpsi = lib.apply_dft_mpo(psi, cutoff=1e-15)
+    want = np.fft.fft(f) / 2 ** (n / 2)
+    assert np.linalg.norm(dense(Fpsi) - want) < 5e-8 * np.linalg.norm(want)
+    back = lib.apply_idft_mpo(Fpsi, cutoff=1e-15)
+    assert np.linalg.norm(dense(back) - f) < 5e-8 * np.linalg.norm(f)
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_fourier_interpolation_and_repeat_function(lib, k):
+    """reference src/fourier_interpolation.jl:1-38 (runtests.jl fourier-interpolation block): a band-limited function on 2^n
+    points is interpolated EXACTLY onto 2^(n+k) points; `repeat_function` tiles it 2^k times.  Compared with the oracle's
+    restatement and with the analytic values."""
+    n = 8
+    x = O.qtt_xrange(n, 0.0, 1.0)
+    f = lambda t: 0.7 * np.cos(2 * np.pi * 3 * t + 0.4) + 0.2 * np.sin(2 * np.pi * 11 * t) + 0.5
+    psi = O.vec_to_mps(f(x), cutoff=1e-15)
+    got = lib.fourier_interpolation(psi, k, cutoff=1e-15)
+    assert len(got) == n + k
+    xf = O.qtt_xrange(n + k, 0.0, 1.0)
+    g = dense(got)
+    assert np.abs(g.imag).max() < 1e-7
+    assert np.abs(g.real - f(xf)).max() < 5e-7
+    want = dense(O.fourier_interpolation(psi, k, cutoff=1e-15))
+    assert np.abs(g - want).max() < 5e-7
+    rep = dense(lib.repeat_function(psi, k, cutoff=1e-15))
+    assert np.abs(rep - np.tile(f(x), 2 ** k)).max() < 5e-7
+    assert np.abs(rep - dense(O.repeat_function(psi, k, cutoff=1e-15))).max() < 5e-7

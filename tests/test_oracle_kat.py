@@ -225,3 +225,21 @@ def test_residual_metric():
     xv = O.mps_to_discrete_function(x); bv = O.mps_to_discrete_function(b)
     assert abs(O.sqeuclidean_mps(A, x, b) - np.sum((Am @ xv - bv) ** 2)) < 1e-12
     assert abs(O.sqeuclidean_normalized_mps(A, x, b) - np.sum((Am @ xv - bv) ** 2) / (bv @ bv)) < 1e-12
+
+
+def test_mirror_dft_mpo_builder_is_the_dft_matrix():
+    """Host operand builder of the drop-in (`itensorqtt.jl_b200/operators.py:dft_mpo`, reference src/dft.jl:81-99): the MPO is
+    the DFT matrix after the output-bit relabelling, to the accuracy its cutoff allows, with the reference's bond profile."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "itensorqtt.jl_b200", "operators.py")
+    spec = importlib.util.spec_from_file_location("qtt_operators_standalone", path)
+    ops = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ops)
+    for n in (1, 2, 4, 9):
+        F = ops.dft_mpo(n)
+        m = O.mpo_to_mat(F, reverse_output_sites=True)
+        assert np.abs(m - O.dft_matrix(n)).max() * 2 ** (n / 2) < 1e-6
+        Fi = ops.idft_mpo(n)
+        mi = O.mpo_to_mat(Fi, reverse_input_sites=True)
+        assert np.abs(mi @ m - np.eye(2 ** n)).max() < 1e-6
+    assert max(O.mpo_linkdims(ops.dft_mpo(20))) <= 11          # SURVEY: DFT MPO bond ~8-11
