@@ -206,7 +206,10 @@ def run_ours(args):
                 "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_kernel (L.v DMMA GEMM + W12 register epilogue) + "
                           "matvec_b_kernel (T2.R DMMA GEMM, in-CTA split-K), the pair timed back to back with CUDA events on "
                           "the library's stream" % chi,
-                "share_of_step": infos[-1]["matvecs"] * mv_ms / ms_per_step,
+                # the sweep's matvec flops expressed in full-size launches x the measured launch time (edge / mid bonds run
+                # smaller, less efficient launches, so this is a lower bound; the ncu launch list gives the kernel pair's share directly)
+                "share_of_step": infos[-1]["flops_matvec"] / f_mv * mv_ms / ms_per_step,
+                "full_size_launch_equivalents_per_step": infos[-1]["flops_matvec"] / f_mv,
                 "flops_per_launch": f_mv, "ms_per_launch": mv_ms,
                 "peak_source": "measured FP64 DMMA.8x8x4 issue rate on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak_dmma_dfma.txt); "
                                "MEASURED_PEAKS.json carries no FP64 entry",

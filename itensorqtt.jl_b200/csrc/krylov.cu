@@ -192,6 +192,8 @@ struct Cgs2Args {
   int per;          // slice length per CTA (even)
   double eta2;      // DGKS threshold eta^2 (0: always reorthogonalise); see cgs2_fused_kernel
   int* counters;    // optional [2]: steps, steps that needed the second pass (trace)
+  int dbgmode;      // development aid (QTT_CGS2_DBGMODE): 1 = return at entry, 2 = return after loading the w slice
+  long long* dbg;   // optional [16]: globaltimer stamps of CTA 0 at the stage boundaries (QTT_CGS2_DBG)
   int kstash;       // the CTA's slices of V[0..kstash) are kept in shared memory after the first pass (read from L2 once, not 4x)
   int post;         // 0: store h1, h2, nrm2 only; 1: GMRES update; 2: Lanczos column
   double a0, a1, tol;
@@ -200,50 +202,67 @@ struct Cgs2Args {
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) { dev::grid_arrive_wait(counter, target); }
+__device__ __forceinline__ void stamp(const Cgs2Args& a, int slot) {
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[slot] = t;
+  }
+}
 
-// MODE 0: V from L2, the first kstash (a multiple of 8) slices are also stashed in shared memory;
-// MODE 1: the stashed slices come from shared memory, the rest from L2.  Groups of 8 vectors are uniform (all stashed
-// or none), so the eight loads of a group are issued back to back before the FMAs.
+// MODE 0: V from L2; the slices of the first kstash vectors are also written to shared memory.
+// MODE 1: the stashed slices come from shared memory, the rest from L2.  Vectors are processed in groups of 8 whose
+// eight loads are issued back to back before the FMAs; the L2 groups of MODE 1 start at kstash.
 template <int MODE>
 __device__ __forceinline__ void slice_dots(const Cgs2Args& a, const double* ws, double* vs, size_t s0, int n2, double* red /*[nwarps][64]*/,
                                            double* part_b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthr = blockDim.x, nwarps = nthr >> 5;
-  for (int i0 = 0; i0 < a.k; i0 += 8) {
-    double acc[8];
+  if (MODE == 1) {
+    for (int i0 = 0; i0 < a.kstash; i0 += 8) {
+      double acc[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-    if (MODE == 1 && i0 < a.kstash) {
+      for (int u = 0; u < 8; ++u) acc[u] = 0.0;
       for (int t2 = tid; t2 < n2; t2 += nthr) {
         const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
         const double* vp = vs + (size_t)i0 * a.per + 2 * t2;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const double2 v = *reinterpret_cast<const double2*>(vp + (size_t)u * a.per);
-          acc[u] += v.x * wv.x + v.y * wv.y;
-        }
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u < a.kstash) {
+            const double2 v = *reinterpret_cast<const double2*>(vp + (size_t)u * a.per);
+            acc[u] += v.x * wv.x + v.y * wv.y;
+          }
       }
-    } else {
-      const bool st = (MODE == 0) && (i0 < a.kstash);
-      for (int t2 = tid; t2 < n2; t2 += nthr) {
-        const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
-        const double* vp = a.V + s0 + 2 * (size_t)t2 + (size_t)i0 * a.len;
-        double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        double v = warp_sum(acc[u]);
+        if (lane == 0 && i0 + u < a.kstash) red[warp * 64 + i0 + u] = v;
+      }
+    }
+  }
+  for (int i0 = (MODE == 1 ? a.kstash : 0); i0 < a.k; i0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    for (int t2 = tid; t2 < n2; t2 += nthr) {
+      const double2 wv = *reinterpret_cast<const double2*>(ws + 2 * t2);
+      const double* vp = a.V + s0 + 2 * (size_t)t2 + (size_t)i0 * a.len;
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)u * a.len)) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += v[u].x * wv.x + v[u].y * wv.y;
+      if (MODE == 0) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)u * a.len)) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] += v[u].x * wv.x + v[u].y * wv.y;
-        if (st) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) *reinterpret_cast<double2*>(vs + (size_t)(i0 + u) * a.per + 2 * t2) = v[u];
-        }
+          if (i0 + u < a.kstash) *reinterpret_cast<double2*>(vs + (size_t)(i0 + u) * a.per + 2 * t2) = v[u];
       }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       double v = warp_sum(acc[u]);
-      if (lane == 0) red[warp * 64 + i0 + u] = v;
+      if (lane == 0 && i0 + u < a.k) red[warp * 64 + i0 + u] = v;
     }
   }
   __syncthreads();
@@ -284,16 +303,17 @@ __device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, const
   for (int t2 = threadIdx.x; t2 < n2; t2 += nthr) {
     double2 x = *reinterpret_cast<const double2*>(ws + 2 * t2);
     const double* vp = a.V + s0 + 2 * (size_t)t2;
-    for (int i0 = 0; i0 < a.k; i0 += 8) {
+    for (int i = 0; i < a.kstash; ++i) {
+      const double2 v = *reinterpret_cast<const double2*>(vs + (size_t)i * a.per + 2 * t2);
+      const double c = h_s[i];
+      x.x -= c * v.x;
+      x.y -= c * v.y;
+    }
+    for (int i0 = a.kstash; i0 < a.k; i0 += 8) {
       double2 v[8];
-      if (i0 < a.kstash) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2*>(vs + (size_t)(i0 + u) * a.per + 2 * t2);
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len)) : make_double2(0.0, 0.0);
-      }
+      for (int u = 0; u < 8; ++u)
+        v[u] = (i0 + u < a.k) ? __ldcg(reinterpret_cast<const double2*>(vp + (size_t)(i0 + u) * a.len)) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
         if (i0 + u < a.k) {
@@ -309,9 +329,12 @@ __device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, const
 constexpr int FT_MAX = 512;
 __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   extern __shared__ double dyn[];
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[13] = a.dbg[11];  // end stamp of the previous launch
+  stamp(a, 12);
+  if (a.dbgmode == 1) return;
   double* ws = dyn;                // [per]
-  double* red = dyn + a.per;       // [32][64]
-  double* h1 = red + 32 * 64;      // [64]
+  double* red = dyn + a.per;       // [nwarps][64]
+  double* h1 = red + (blockDim.x >> 5) * 64;  // [64]
   double* h2 = h1 + 64;            // [64]
   double* vs = h2 + 64;            // [kstash][per] stashed slices of V
   __shared__ double nred[FT_MAX / 32];
@@ -339,9 +362,12 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
       s_r0n2 = a.S[kscal::S_R0N2];
     }
   }
+  stamp(a, 0);
   for (int t2 = tid; t2 < n2; t2 += nthr)
     *reinterpret_cast<double2*>(ws + 2 * t2) = __ldcg(reinterpret_cast<const double2*>(a.w + s0 + 2 * (size_t)t2));
   __syncthreads();
+  stamp(a, 1);
+  if (a.dbgmode == 2) return;
   double* P1 = a.part;
   double* P2 = a.part + (size_t)G * 64;
   double* P3 = a.part + (size_t)2 * G * 64;
@@ -363,8 +389,11 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   };
   if (a.eta2 > 0.0) block_norm2(P1 + (size_t)b * 64 + 63);
   slice_dots<0>(a, ws, vs, s0, n2, red, P1 + (size_t)b * 64);
+  stamp(a, 2);
   grid_barrier(a.bar, a.epoch + (unsigned)G);
+  stamp(a, 3);
   reduce_partials(P1, a.k, G, h1);
+  stamp(a, 4);
   // DGKS test (Daniel-Gragg-Kaufman-Stewart): the second Gram-Schmidt pass is only needed when the first one cancelled
   // most of w.  |w'|^2 is ESTIMATED by Pythagoras, |w|^2 - |h1|^2, for the decision only (identical in every CTA: the
   // inputs are the fixed-order reductions); the norm that is used afterwards is computed from the actual vector.
@@ -385,12 +414,16 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
   }
   slice_axpys(a, ws, vs, s0, n2, h1);
   __syncthreads();
+  stamp(a, 5);
   if (second) {
     slice_dots<1>(a, ws, vs, s0, n2, red, P2 + (size_t)b * 64);
+    stamp(a, 6);
     grid_barrier(a.bar, a.epoch + 2u * (unsigned)G);
+    stamp(a, 7);
     reduce_partials(P2, a.k, G, h2);
     slice_axpys(a, ws, vs, s0, n2, h2);
     __syncthreads();
+    stamp(a, 8);
   } else {
     if (tid < 64) h2[tid] = 0.0;
     // keep the barrier counter in step with the host's bookkeeping (3 arrivals per CTA per launch)
@@ -400,8 +433,12 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
     atomicAdd(a.counters, 1);
     if (second) atomicAdd(a.counters + 1, 1);
   }
+  // (|w''|^2 = |w'|^2 - |h2|^2 reduced together with the second dots would save this pass and barrier; measured: the
+  // extra reduction work costs most of what the barrier saves -- 1 us of a 25 us step -- so the norm stays exact.)
   block_norm2(P3 + b);
+  stamp(a, 9);
   grid_barrier(a.bar, a.epoch + 3u * (unsigned)G);
+  stamp(a, 10);
   if (warp == 0) {
     double s = 0.0;
     for (int bb = lane; bb < G; bb += 32) s += __ldcg(P3 + bb);
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
     __stcg(reinterpret_cast<double2*>(a.w + s0 + 2 * (size_t)t2), x);
     if (a.vnext) __stcg(reinterpret_cast<double2*>(a.vnext + s0 + 2 * (size_t)t2), make_double2(x.x * inv, x.y * inv));
   }
+  stamp(a, 11);
   if (b == 0 && a.S != nullptr) {
     if (tid < a.k) {
       a.S[a.off_h1 + tid] = h1[tid];
@@ -529,21 +567,24 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   if (G < 1) G = 1;
   size_t per = (len + G - 1) / G;
   per = (per + 1) & ~size_t(1);
-  const size_t base = per + 32 * 64 + 128;  // doubles: w slice, reduction scratch, h1, h2
-  static const bool stash = !(getenv("QTT_CGS2_STASH") && atoi(getenv("QTT_CGS2_STASH")) == 0);
+  static const int fthreads = getenv("QTT_CGS2_THREADS") ? atoi(getenv("QTT_CGS2_THREADS")) : 512;
+  const size_t base = per + (size_t)(fthreads / 32) * 64 + 128;  // doubles: w slice, reduction scratch, h1, h2
+  // stash budget: the whole 227 KB of the SM minus the kernel's static shared memory (one CTA per SM anyway); at
+  // chi = 256 this holds the CTA's slices of 14 basis vectors (a 200 KB budget and whole groups of 8 held only 8)
+  constexpr size_t SMEM_BUDGET = 227 * 1024 - 2048;
+  static const int stash_cap = getenv("QTT_CGS2_STASH") ? atoi(getenv("QTT_CGS2_STASH")) : 64;
   int kstash = 0;
-  if (stash) {
-    const size_t room = (size_t)(200 * 1024) / sizeof(double) - base;
+  if (stash_cap > 0 && SMEM_BUDGET / sizeof(double) > base) {
+    const size_t room = SMEM_BUDGET / sizeof(double) - base;
     kstash = (int)(room / per);
     if (kstash > k) kstash = k;
-    kstash &= ~7;  // whole groups of 8 vectors
+    if (kstash > stash_cap) kstash = stash_cap;
   }
   const size_t smem = (base + (size_t)kstash * per) * sizeof(double);
-  static const int fthreads = getenv("QTT_CGS2_THREADS") ? atoi(getenv("QTT_CGS2_THREADS")) : 512;
   static size_t configured = 0;
   if (smem > configured) {
-    QTT_CUDA(cudaFuncSetAttribute(cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    configured = 200 * 1024;
+    QTT_CUDA(cudaFuncSetAttribute(cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    configured = SMEM_BUDGET;
   }
   Cgs2Args a;
   a.V = V; a.k = k; a.len = len; a.w = w; a.vnext = vnext; a.S = S;
@@ -555,14 +596,38 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   static const double eta = getenv("QTT_DGKS_ETA") ? atof(getenv("QTT_DGKS_ETA")) : 0.0;
   a.eta2 = eta * eta;
   a.counters = nullptr;
+  a.dbg = nullptr;
+  static const int dbgmode = getenv("QTT_CGS2_DBGMODE") ? atoi(getenv("QTT_CGS2_DBGMODE")) : 0;
+  a.dbgmode = dbgmode;
+  static const bool dbg_on = getenv("QTT_CGS2_DBG") != nullptr;
+  static long long* dbg_dev = nullptr;
+  static int dbg_calls = 0;
+  if (dbg_on) {
+    if (!dbg_dev) QTT_CUDA(cudaMalloc(&dbg_dev, 16 * sizeof(long long)));
+    a.dbg = dbg_dev;
+  }
   a.post = post;
   a.a0 = a0; a.a1 = a1; a.tol = tol; a.hstat = hstat;
   a.off_h1 = off_h1; a.off_h2 = off_h2; a.off_nres2 = off_nres2; a.off_done = off_done;
   // cooperative launch: the grid barriers need every CTA resident (measured: no extra launch cost over <<< >>>)
   void* args[] = {&a};
-  QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
+  static const bool plain_launch = getenv("QTT_CGS2_PLAIN") != nullptr;
+  if (plain_launch) {
+    cgs2_fused_kernel<<<G, fthreads, smem, ctx->stream>>>(a);
+    QTT_CUDA(cudaGetLastError());
+  } else {
+    QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
+  }
   ctx->launches++;
-  ctx->bar_epoch += 3u * (unsigned)G;
+  if (!dbgmode) ctx->bar_epoch += 3u * (unsigned)G;
+  if (dbg_on && (++dbg_calls % 97) == 0) {  // development aid: stage times of CTA 0 (ns since the kernel's first stamp)
+    long long h[16];
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+    QTT_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[cgs2 dbg] k=%d G=%d kstash=%d: load_w %lld dots1 %lld bar1 %lld red1 %lld axpy1 %lld dots2 %lld bar2 %lld red2+axpy2 %lld norm %lld bar3 %lld store %lld | gap since previous launch's end stamp %lld, prologue %lld ns\n",
+            k, G, kstash, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8],
+            h[10] - h[9], h[11] - h[10], h[12] - h[13], h[0] - h[12]);
+  }
 }
 
 }  // namespace qtt
