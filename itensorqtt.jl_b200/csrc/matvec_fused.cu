@@ -254,9 +254,9 @@ struct MvBArgs {
   long lda, ldb, ldc;
 };
 
-template <int VEC>
+template <int VEC, int BN>
 __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
-  constexpr int BM = 32, BN = 64, NT = 256;
+  constexpr int BM = 32, NT = 256, NJ = BN / 16;  // each warp of a K-group owns 16 rows x BN/2 columns
   constexpr int A_LD = BK + 4, B_LD = BN + 4;
   constexpr int A_STAGE = BM * A_LD, B_STAGE = BK * B_LD;
   constexpr int ST = 6;  // stages; two k-tiles (one per K-group) are consumed per barrier
@@ -267,14 +267,14 @@ __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
   const int g = lane >> 2, t = lane & 3;
   const int kg = warp >> 2;           // K-group
   const int w4 = warp & 3;
-  const int wm0 = (w4 >> 1) * 16, wn0 = (w4 & 1) * 32;
+  const int wm0 = (w4 >> 1) * 16, wn0 = (w4 & 1) * (BN / 2);
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
-  double acc[2][4][2];
+  double acc[2][NJ][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = (p.K + BK - 1) / BK;
   constexpr int A_CPR = BK / VEC, A_TOTAL = BM * A_CPR, NA = (A_TOTAL + NT - 1) / NT;
@@ -371,15 +371,15 @@ __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
         const double* bs = Bs + st_use * B_STAGE + b_frag;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-          double a[2], b[4];
+          double a[2], b[NJ];
 #pragma unroll
           for (int i = 0; i < 2; ++i) a[i] = as[(i * 8) * A_LD + kk * 4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] = bs[(kk * 4) * B_LD + j * 8];
+          for (int j = 0; j < NJ; ++j) b[j] = bs[(kk * 4) * B_LD + j * 8];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
       }
       st_use = (st_use + 2 >= ST) ? st_use + 2 - ST : st_use + 2;
@@ -390,13 +390,13 @@ __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
   else run(FalseT{});
   __syncthreads();
   // combine the two K-groups: group 1 parks its tile in shared memory, group 0 adds (fixed order) and stores
-  double* red = smem;  // [4 warps][2][4][32 lanes] double2
+  double* red = smem;  // [4 warps][2][NJ][32 lanes] double2
   if (kg == 1) {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<double2*>(red + (((w4 * 2 + i) * 4 + j) * 32 + lane) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+      for (int j = 0; j < NJ; ++j)
+        *reinterpret_cast<double2*>(red + (((w4 * 2 + i) * NJ + j) * 32 + lane) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
   }
   __syncthreads();
   if (kg == 0) {
@@ -404,8 +404,8 @@ __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
     for (int i = 0; i < 2; ++i) {
       const int row = m0 + wm0 + i * 8 + g;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double2 o = *reinterpret_cast<const double2*>(red + (((w4 * 2 + i) * 4 + j) * 32 + lane) * 2);
+      for (int j = 0; j < NJ; ++j) {
+        const double2 o = *reinterpret_cast<const double2*>(red + (((w4 * 2 + i) * NJ + j) * 32 + lane) * 2);
         const double v0 = acc[i][j][0] + o.x, v1 = acc[i][j][1] + o.y;
         const int col = n0 + wn0 + j * 8 + 2 * t;
         if (row < p.M && col < p.N) {
@@ -446,9 +446,13 @@ template <int WL, int VEC>
 void launch_mva_shape(Ctx* ctx, const MvAArgs& a) {
   int shape = g_mva_shape;
   if (shape < 0) {
-    // 8 warps (footprint 32 x 16) once that yields enough CTAs for most SMs; otherwise 4 warps (16 x 16)
+    // 4 warps with a 16 x 16 footprint (two to three CTAs resident per SM hide each other's barriers and pipeline fills):
+    // measured faster than 8 warps / 32 x 16 at chi = 128 ... 256 and 512 (20.1 vs 20.0, 27.8 vs 26.2 TFLOP/s at w = 3; in the
+    // sweep 127.2 vs 128.8 ms) -- except where the 32 x 16 tiles fill exactly one wave of two CTAs per SM (chi = 384:
+    // 27.3 vs 24.8 TFLOP/s).  profiles/r01_bench.md
     const long big = (long)((a.chil + 31) / 32) * ((a.chir + 15) / 16);
-    shape = (big >= (long)(ctx->sms * 3) / 4) ? 0 : 1;
+    const bool one_full_wave = big * 10 > (long)ctx->sms * 2 * 9 && big <= (long)ctx->sms * 2;
+    shape = one_full_wave ? 0 : 1;
   }
   if (shape == 0) launch_mva<WL, 1, 4, 2, VEC>(ctx, a);
   else if (shape == 1) launch_mva<WL, 1, 2, 2, VEC>(ctx, a);
@@ -491,22 +495,31 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
   b.M = 4 * chil; b.N = chir; b.K = wr * chir;
   b.lda = (long)wr * chir; b.ldb = chir; b.ldc = chir;
   const bool vecB = (chir % 2 == 0) && al16(T2) && al16(R) && al16(out);
-  // the request is padded to > half of an SM's shared memory so that at most ONE matvec_b CTA is resident per SM: with
-  // programmatic dependent launch the early CTAs would otherwise pile up two-deep on the SMs that matvec_a leaves idle
-  constexpr size_t smemB_used = (size_t)6 * (32 * (BK + 4) + BK * (64 + 4)) * sizeof(double);
-  constexpr size_t smemB_max = smemB_used > 116 * 1024 ? smemB_used : 116 * 1024;
+  // 32 x 32 tiles (twice the CTAs, two to three resident per SM) for small outputs, where 32 x 64 tiles leave most SMs
+  // idle (chi = 128, w = 4: 18.6 vs 24.7 us), and for multi-wave outputs, where they balance better (chi = 512: 29.6 vs
+  // 27.9 TFLOP/s); 32 x 64 tiles for the single-wave sizes in between (chi = 256: 21.1 vs 17.4 TFLOP/s).  For the
+  // 32 x 64 single-wave case the request is padded to > half of an SM's shared memory so that at most ONE CTA is
+  // resident per SM: with programmatic dependent launch the early CTAs would otherwise pile up two-deep on the SMs that
+  // matvec_a leaves idle.
+  constexpr size_t smemB64 = (size_t)6 * (32 * (BK + 4) + BK * (64 + 4)) * sizeof(double);
+  constexpr size_t smemB32 = (size_t)6 * (32 * (BK + 4) + BK * (32 + 4)) * sizeof(double);
+  constexpr size_t smemB_max = smemB64 > 116 * 1024 ? smemB64 : 116 * 1024;
   static bool configured = false;
   if (!configured) {
-    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
-    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+    QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     configured = true;
   }
   {
+    const long ctas64 = (long)((b.M + 31) / 32) * ((b.N + 63) / 64);
+    static const int bn_env = getenv("QTT_MVB_BN") ? atoi(getenv("QTT_MVB_BN")) : 0;
+    const int bn = bn_env ? bn_env : ((ctas64 * 4 < (long)ctx->sms * 3 || ctas64 >= 2L * ctx->sms) ? 32 : 64);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((b.M + 31) / 32, (b.N + 63) / 64);
+    cfg.gridDim = dim3((b.M + 31) / 32, (b.N + bn - 1) / bn);
     cfg.blockDim = dim3(256);
-    const long ctas_b = (long)((b.M + 31) / 32) * ((b.N + 63) / 64);
-    cfg.dynamicSmemBytes = ctas_b <= ctx->sms ? smemB_max : smemB_used;  // single wave: one CTA per SM (see above)
+    cfg.dynamicSmemBytes = bn == 32 ? smemB32 : (ctas64 <= ctx->sms ? smemB_max : smemB64);
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -514,8 +527,13 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
     cfg.attrs = attr;
     static const bool pdl = !(getenv("QTT_PDL") && atoi(getenv("QTT_PDL")) == 0);
     cfg.numAttrs = pdl ? 1 : 0;
-    if (vecB) QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<2>, b));
-    else QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<1>, b));
+    if (bn == 32) {
+      if (vecB) QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<2, 32>, b));
+      else QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<1, 32>, b));
+    } else {
+      if (vecB) QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<2, 64>, b));
+      else QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<1, 64>, b));
+    }
   }
   check_launch(ctx, "matvec_b");
 }
