@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(PANEL_THREADS) dqr_panel_kernel(PanelArgs a) {
       }
     }
     target += G;
-    dev::grid_arrive_wait(a.bar, target);
+    if (G > 1) dev::grid_arrive_wait(a.bar, target);
+    else __syncthreads();
     // reduce (same order in every CTA)
     for (int c = jj + warp; c < nb; c += NW) {
       double v = 0.0;
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(PANEL_THREADS) dqr_panel_kernel(PanelArgs a) {
     if (lane == 0) gram_part[(size_t)g * 1024 + x * DNB + y] = acc;
   }
   target += G;
-  dev::grid_arrive_wait(a.bar, target);
+  if (G > 1) dev::grid_arrive_wait(a.bar, target);
+  else __syncthreads();
   if (g != 0) return;
   for (int e = tid; e < nb * nb; e += PANEL_THREADS) {
     const int x = e / nb, y = e % nb;
@@ -376,7 +378,7 @@ void dense_qr_rows(Ctx* ctx, double* base, const DenseLayout& d, int n, int nrow
     const int nb = n - j0 < DNB ? n - j0 : DNB;
     {
       const int K = m - j0;
-      int G = K / 128;
+      int G = K <= 512 ? 1 : K / 128;  // small panels: one CTA, the whole panel in shared memory, no grid barrier
       if (G < 1) G = 1;
       if (G > PANEL_G_MAX) G = PANEL_G_MAX;
       if (G > ctx->sms) G = ctx->sms;
@@ -394,7 +396,7 @@ void dense_qr_rows(Ctx* ctx, double* base, const DenseLayout& d, int n, int nrow
       void* args[] = {&pa};
       QTT_CUDA(cudaLaunchCooperativeKernel((void*)dqr_panel_kernel, dim3(G), dim3(PANEL_THREADS), args, smem, ctx->stream));
       ctx->launches++;
-      ctx->dense_epoch += (unsigned)G * (unsigned)(nb + 1);
+      if (G > 1) ctx->dense_epoch += (unsigned)G * (unsigned)(nb + 1);
     }
     const int nrem = nrow - (j0 + nb);
     if (nrem <= 0) continue;

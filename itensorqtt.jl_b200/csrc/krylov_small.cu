@@ -22,6 +22,7 @@ constexpr int SLD = 32;  // leading dimension of the Hessenberg/R matrix (krylov
 constexpr int S_DOUBLES = OFF_R + SLD * SLD;
 
 struct SmallArgs {
+  int vstash;          // basis vectors kept in shared memory
   const double* L;     // [wl][chil][chil]
   const double* W12;   // [4 wl][4 wr]
   const double* R;     // [wr][chir][chir]
@@ -92,44 +93,65 @@ __device__ double block_sum(double v, double* red) {
   return s;
 }
 
-// out[e] (+)= sum_{i<k} coef[i] V[i][e] with 8 independent L2 loads in flight per thread (a single CTA is latency bound)
-__device__ __forceinline__ double comb8(const double* V, int k, int len, int e, const double* coef, double sign) {
+// The Krylov basis: the first `ns` vectors live in shared memory (as many as fit next to the operator), the others in
+// global memory (L2).  A single CTA is latency bound on the L2 part, so its loads are issued in batches of 16.
+struct Basis {
+  double* g;   // global [(kd + 1)][len]; slots < ns unused
+  double* s;   // shared [ns][len]
+  int ns, len;
+  __device__ __forceinline__ double ld(int i, int e) const { return i < ns ? s[(size_t)i * len + e] : __ldcg(g + (size_t)i * len + e); }
+  __device__ __forceinline__ void st(int i, int e, double v) const {
+    if (i < ns) s[(size_t)i * len + e] = v;
+    else g[(size_t)i * len + e] = v;
+  }
+};
+
+// sum_{i<k} coef[i] V[i][e]
+__device__ __forceinline__ double comb(const Basis& B, int k, int e, const double* coef, double sign) {
   double x = 0.0;
-  for (int i0 = 0; i0 < k; i0 += 8) {
-    double v[8];
+  const int ks = k < B.ns ? k : B.ns;
+  for (int i = 0; i < ks; ++i) x += coef[i] * B.s[(size_t)i * B.len + e];
+  for (int i0 = ks; i0 < k; i0 += 16) {
+    double v[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = (i0 + u < k) ? __ldcg(V + (size_t)(i0 + u) * len + e) : 0.0;
+    for (int u = 0; u < 16; ++u) v[u] = (i0 + u < k) ? __ldcg(B.g + (size_t)(i0 + u) * B.len + e) : 0.0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 16; ++u)
       if (i0 + u < k) x += coef[i0 + u] * v[u];
   }
   return sign * x;
 }
 
 // h[i] = V[i] . w for i < k; then w -= V h   (one classical Gram-Schmidt pass)
-__device__ void cgs_pass(const double* V, int k, int len, double* w, double* h) {
+__device__ void cgs_pass(const Basis& B, int k, double* w, double* h) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int len = B.len;
   for (int i = warp; i < k; i += ST / 32) {
-    const double* vi = V + (size_t)i * len;
     double acc = 0.0;
-    for (int e0 = 0; e0 < len; e0 += 256) {
-      double v[8];
+    if (i < B.ns) {
+      const double* vi = B.s + (size_t)i * len;
+      for (int e = lane; e < len; e += 32) acc += vi[e] * w[e];
+    } else {
+      const double* vi = B.g + (size_t)i * len;
+      for (int e0 = 0; e0 < len; e0 += 512) {
+        double v[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + lane + 32 * u;
-        v[u] = e < len ? __ldcg(vi + e) : 0.0;
-      }
+        for (int u = 0; u < 16; ++u) {
+          const int e = e0 + lane + 32 * u;
+          v[u] = e < len ? __ldcg(vi + e) : 0.0;
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + lane + 32 * u;
-        if (e < len) acc += v[u] * w[e];
+        for (int u = 0; u < 16; ++u) {
+          const int e = e0 + lane + 32 * u;
+          if (e < len) acc += v[u] * w[e];
+        }
       }
     }
     acc = warp_sum(acc);
     if (lane == 0) h[i] = acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < len; e += ST) w[e] += comb8(V, k, len, e, h, -1.0);
+  for (int e = threadIdx.x; e < len; e += ST) w[e] += comb(B, k, e, h, -1.0);
   __syncthreads();
 }
 
@@ -150,6 +172,8 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
   m.S = p; p += S_DOUBLES;
   m.h = p; p += 128;
   m.red = p; p += 32;
+  Basis B;
+  B.g = a.V; B.s = p; B.ns = a.vstash; B.len = len;
   for (int i = tid; i < wl * chil * chil; i += ST) m.L[i] = a.L[i];
   for (int i = tid; i < wr * chir * chir; i += ST) m.R[i] = a.R[i];
   for (int i = tid; i < 16 * wl * wr; i += ST) m.W[i] = a.W12[i];
@@ -157,7 +181,7 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
   for (int i = tid; i < len; i += ST) m.v[i] = a.x[i];
   __syncthreads();
   double* S = m.S;
-  double* r0 = a.V + (size_t)a.kd * len;  // the slot of v_kd doubles as the residual buffer between cycles
+  const int r0 = a.kd;  // the slot of v_kd doubles as the residual buffer between cycles
   const bool fixed = a.fixed != 0;
   const double tol = fixed ? -1.0 : a.tol;
   double matvecs = 0.0, resid = 0.0, converged = 0.0;
@@ -168,7 +192,7 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
   double acc = 0.0;
   for (int e = tid; e < len; e += ST) {
     const double r = a.beff[e] - a.a0 * m.v[e] - a.a1 * m.w[e];
-    r0[e] = r;
+    B.st(r0, e, r);
     acc += r * r;
   }
   double r0n2 = block_sum(acc, m.red);
@@ -186,8 +210,8 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
       const double inv = d != 0.0 ? 1.0 / d : 0.0;
       __syncthreads();
       for (int e = tid; e < len; e += ST) {
-        const double v0 = r0[e] * inv;
-        a.V[e] = v0;
+        const double v0 = B.ld(r0, e) * inv;
+        B.st(0, e, v0);
         m.v[e] = v0;
       }
     }
@@ -196,8 +220,8 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
     for (int k = 1; k <= a.kd; ++k) {
       small_matvec(m, chil, chir, wl, wr);
       matvecs += 1.0;
-      cgs_pass(a.V, k, len, m.w, S + OFF_H1);
-      cgs_pass(a.V, k, len, m.w, S + OFF_H2);
+      cgs_pass(B, k, m.w, S + OFF_H1);
+      cgs_pass(B, k, m.w, S + OFF_H2);
       double na = 0.0;
       for (int e = tid; e < len; e += ST) na += m.w[e] * m.w[e];
       const double n2 = block_sum(na, m.red);
@@ -209,10 +233,9 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
       const bool dead = S[S_DONE] != 0.0;
       const double nrm = sqrt(n2);
       const double inv = (nrm != 0.0 && !dead) ? 1.0 / nrm : 0.0;
-      double* vk = a.V + (size_t)k * len;
       for (int e = tid; e < len; e += ST) {
         const double vv = m.w[e] * inv;
-        vk[e] = vv;
+        B.st(k, e, vv);
         m.v[e] = vv;
       }
       ksteps = k;
@@ -223,15 +246,15 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
     const int kfin = fixed ? a.kd : (int)S[S_K];
     if (tid == 0) gmres_solve_scalars(S, fixed ? -a.kd : kfin, SLD);
     __syncthreads();
-    for (int e = tid; e < len; e += ST) a.x[e] += comb8(a.V, kfin, len, e, S + OFF_YK, 1.0);
+    for (int e = tid; e < len; e += ST) a.x[e] += comb(B, kfin, e, S + OFF_YK, 1.0);
     __syncthreads();
     resid = S[S_BETA];
     if (fixed) break;
     if (resid > a.tol) {
       // restart residual as the explicit combination of the basis (no extra operator application)
-      for (int e = tid; e < len; e += ST) m.w[e] = comb8(a.V, kfin + 1, len, e, S + OFF_COEF, 1.0);
+      for (int e = tid; e < len; e += ST) m.w[e] = comb(B, kfin + 1, e, S + OFF_COEF, 1.0);
       __syncthreads();
-      for (int e = tid; e < len; e += ST) r0[e] = m.w[e];
+      for (int e = tid; e < len; e += ST) B.st(r0, e, m.w[e]);
       __syncthreads();
     } else {
       for (int e = tid; e < len; e += ST) m.v[e] = a.x[e];
@@ -241,7 +264,7 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
       double ra = 0.0;
       for (int e = tid; e < len; e += ST) {
         const double r = a.beff[e] - a.a0 * m.v[e] - a.a1 * m.w[e];
-        r0[e] = r;
+        B.st(r0, e, r);
         ra += r * r;
       }
       const double n2 = block_sum(ra, m.red);
@@ -259,6 +282,8 @@ __global__ void __launch_bounds__(ST) gmres_small_kernel(SmallArgs a) {
     a.stats[3] = S[S_BETA];
   }
 }
+
+constexpr size_t SMALL_SMEM_BUDGET = 224 * 1024;  // dynamic shared memory of the single CTA (227 KB minus static)
 
 size_t small_smem_doubles(int chil, int chir, int wl, int wr) {
   const size_t len = (size_t)4 * chil * chir;
@@ -279,7 +304,7 @@ void gmres_small(Ctx* ctx, const double* L, const double* W12, const double* R, 
                  int wr, double a0, double a1, double tol, int kd, int maxiter, bool fixed, double* V, double* stats_dev) {
   static bool configured = false;
   if (!configured) {
-    QTT_CUDA(cudaFuncSetAttribute(gmres_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QTT_CUDA(cudaFuncSetAttribute(gmres_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_BUDGET));
     configured = true;
   }
   SmallArgs a;
@@ -287,7 +312,13 @@ void gmres_small(Ctx* ctx, const double* L, const double* W12, const double* R, 
   a.chil = chil; a.chir = chir; a.wl = wl; a.wr = wr;
   a.a0 = a0; a.a1 = a1; a.tol = tol; a.kd = kd; a.maxiter = maxiter; a.fixed = fixed ? 1 : 0;
   a.stats = stats_dev;
-  const size_t smem = small_smem_doubles(chil, chir, wl, wr) * sizeof(double);
+  // as many basis vectors as fit stay in shared memory (all kd + 1 of them for len <= 512 at krylovdim 30)
+  const size_t base = small_smem_doubles(chil, chir, wl, wr);
+  const size_t len = (size_t)4 * chil * chir;
+  size_t ns = (SMALL_SMEM_BUDGET / sizeof(double) - base) / len;
+  if (ns > (size_t)kd + 1) ns = (size_t)kd + 1;
+  a.vstash = (int)ns;
+  const size_t smem = (base + ns * len) * sizeof(double);
   gmres_small_kernel<<<1, ST, smem, ctx->stream>>>(a);
   check_launch(ctx, "gmres_small");
 }
