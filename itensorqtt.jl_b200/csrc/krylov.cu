@@ -560,8 +560,9 @@ bool kry_cgs2_fused_ok(const Ctx* ctx, size_t len) {
 void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, double* vnext, double* S, int off_h1, int off_h2,
                     int off_nres2, int off_done, int post, double a0, double a1, double tol, volatile double* hstat) {
   QTT_REQUIRE(k >= 1 && k <= 64, "kry_cgs2_fused: k out of range");
-  // one CTA per >= 1024 elements: short vectors (edge / mid bonds) use few CTAs, whose grid barriers are cheaper
-  static const int min_per = getenv("QTT_CGS2_MINPER") ? atoi(getenv("QTT_CGS2_MINPER")) : 1024;
+  // one CTA per >= 512 elements: short vectors (edge / mid bonds) use few CTAs, whose grid barriers are cheaper (measured
+  // at len = 16384 / 65536, k = 30: 25.2 / 27.7 us with 512, 30.3 / 31.8 us with 1024, no gain below 512)
+  static const int min_per = getenv("QTT_CGS2_MINPER") ? atoi(getenv("QTT_CGS2_MINPER")) : 512;
   int G = (int)((len + min_per - 1) / min_per);
   if (G > ctx->sms) G = ctx->sms;
   if (G < 1) G = 1;
