@@ -90,6 +90,18 @@ struct Ctx {
   double* partial(size_t n);
 };
 
+// cudaFuncSetAttribute is a per-DEVICE setting: a call site configures its kernel once per device, not once per process
+// (one process may drive several GPUs through several contexts).
+struct DevOnce {
+  bool done[64] = {};
+  bool first(int dev) {
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 inline void check_launch(Ctx* c, const char* what) {
   c->launches++;
   cudaError_t e = cudaGetLastError();

@@ -214,10 +214,9 @@ template <int BM, int BN, int WM, int WN, int STAGES, bool TA, bool TB, int VEC>
 void launch_cfg(Ctx* ctx, const GemmArgs& a, int batch_total) {
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, STAGES, TA, TB, VEC>;
   constexpr size_t smem = smem_bytes<BM, BN, STAGES, TA, TB>();
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, batch_total);
   kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(a);

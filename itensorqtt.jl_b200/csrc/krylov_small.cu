@@ -302,10 +302,9 @@ bool gmres_small_ok(int chil, int chir, int wl, int wr, int kd) {
 // V: workspace of (kd + 1) * len doubles; stats_dev: 4 doubles (matvecs, resid, converged, beta)
 void gmres_small(Ctx* ctx, const double* L, const double* W12, const double* R, const double* beff, double* x, int chil, int chir, int wl,
                  int wr, double a0, double a1, double tol, int kd, int maxiter, bool fixed, double* V, double* stats_dev) {
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     QTT_CUDA(cudaFuncSetAttribute(gmres_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_BUDGET));
-    configured = true;
   }
   SmallArgs a;
   a.L = L; a.W12 = W12; a.R = R; a.beff = beff; a.x = x; a.V = V;

@@ -430,10 +430,9 @@ template <int WL, int MI, int WM, int WN, int VEC>
 void launch_mva(Ctx* ctx, const MvAArgs& a) {
   auto kern = matvec_a_kernel<WL, MI, WM, WN, VEC>;
   constexpr size_t smem = mva_smem<WL, MI, WM, WN>();
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid((a.chil + 8 * MI * WM - 1) / (8 * MI * WM), (a.chir + 8 * WN - 1) / (8 * WN));
   kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(a);
@@ -504,13 +503,12 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
   constexpr size_t smemB64 = (size_t)6 * (32 * (BK + 4) + BK * (64 + 4)) * sizeof(double);
   constexpr size_t smemB32 = (size_t)6 * (32 * (BK + 4) + BK * (32 + 4)) * sizeof(double);
   constexpr size_t smemB_max = smemB64 > 116 * 1024 ? smemB64 : 116 * 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
-    configured = true;
   }
   {
     const long ctas64 = (long)((b.M + 31) / 32) * ((b.N + 63) / 64);

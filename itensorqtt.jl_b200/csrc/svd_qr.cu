@@ -754,10 +754,9 @@ __global__ void __launch_bounds__(64 * JBT) jacobi_qr_block_kernel(JqArgs a) {
 
 template <int NC, int JBT>
 void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC, JBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
   }
   void* args[] = {&a};
   QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC, JBT>, dim3(grid), dim3(64 * JBT), args, smem, ctx->stream));
@@ -835,13 +834,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   const int nb = panel_width(p);
   const size_t smem_panel = ((size_t)nb * ldp + q) * sizeof(double);
   const size_t smem_apply = (size_t)nb * ldp * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce once;
+  if (once.first(ctx->device)) {
     set_smem(qr_panel_kernel, 200 * 1024);
     set_smem(qr_apply_kernel<8>, 200 * 1024);
     set_smem(qr_apply_kernel<16>, 200 * 1024);
     set_smem(qr_apply_kernel<32>, 200 * 1024);
-    configured = true;
   }
   const int npanels = (kmax + nb - 1) / nb;
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;

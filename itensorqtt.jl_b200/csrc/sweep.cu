@@ -236,10 +236,9 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
   const bool fused = kry_cgs2_fused_ok(ctx, len);
   auto run_ritz = [&]() {
     constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static DevOnce once;
+    if (once.first(ctx->device)) {
       QTT_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRitzSmem));
-      configured = true;
     }
     ritz_kernel<<<1, 32, kRitzSmem, ctx->stream>>>(S, kd, 64, target, which, S + OFF_YK);
     check_launch(ctx, "ritz");
