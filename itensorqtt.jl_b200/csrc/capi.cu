@@ -465,6 +465,20 @@ int qtt_vec_to_mps(qtt_ctx* ctx, const double* v, int32_t n, int32_t on_device, 
   QTT_REQUIRE(n >= 1 && n <= 34, "qtt_vec_to_mps: n = %d out of range [1, 34]", n);
   QTT_CUDA(cudaSetDevice(ctx->device));
   const size_t total = (size_t)1 << n;
+  {
+    // the caller states where v lives; a mismatch would otherwise surface as an illegal address inside a kernel
+    cudaPointerAttributes pa;
+    const cudaError_t e = cudaPointerGetAttributes(&pa, v);
+    cudaGetLastError();
+    const bool is_dev = (e == cudaSuccess) && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    if (on_device) {
+      QTT_REQUIRE(is_dev, "qtt_vec_to_mps: on_device = 1 but v is not a device pointer");
+      QTT_REQUIRE(pa.type == cudaMemoryTypeManaged || pa.device == ctx->device, "qtt_vec_to_mps: v lives on device %d, the context on device %d",
+                  pa.device, ctx->device);
+    } else {
+      QTT_REQUIRE(!(e == cudaSuccess && pa.type == cudaMemoryTypeDevice), "qtt_vec_to_mps: on_device = 0 but v is a device pointer");
+    }
+  }
   double* staged = nullptr;
   if (!on_device) {
     staged = static_cast<double*>(pool_alloc(total * sizeof(double), ctx->stream));

@@ -100,3 +100,10 @@ def test_device_resident_samples_and_edges(lib):
     assert np.abs(_dense(z)).max() == 0.0
     with pytest.raises(ValueError):
         lib.vec_to_mps(np.ones(12))
+    # the residency flag is checked against the pointer instead of faulting inside a kernel
+    import ctypes as C
+    out, err = C.c_void_p(), C.c_double()
+    host = np.ones(8)
+    ctx = lib.default_context()
+    rc = lib.lib.qtt_vec_to_mps(ctx.handle, C.c_void_p(host.ctypes.data), 3, 1, 1e-15, 0, 1, C.byref(out), C.byref(err))
+    assert rc != 0 and b"not a device pointer" in lib.lib.qtt_last_error(ctx.handle)
