@@ -12,6 +12,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// First statement of every kernel that launch_pdl() (common.cuh) may launch programmatically behind its producer: blocks until
+// the preceding grid has completed and its memory is visible; a no-op under a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p));

@@ -13,6 +13,7 @@
 // Global -> shared staging is a STAGES-deep cp.async (LDGSTS) pipeline with zero-fill predication, so
 // ragged edge bonds (chi = 1, 2, 3, ... and odd MPO bond dimensions) take the same code path.
 #include "common.cuh"
+#include "device_utils.cuh"
 
 namespace qtt {
 
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gemm_dmma_kernel(GemmAr
   constexpr int B_ROWS = TB ? BN : BK, B_COLS = TB ? BK : BN, B_LD = B_COLS + 4;
   constexpr int A_STAGE = A_ROWS * A_LD, B_STAGE = B_ROWS * B_LD;
 
+  dev::pdl_wait();
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
@@ -219,8 +221,7 @@ void launch_cfg(Ctx* ctx, const GemmArgs& a, int batch_total) {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, batch_total);
-  kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(a);
-  check_launch(ctx, "gemm_dmma");
+  launch_pdl(ctx, "gemm_dmma", kern, grid, dim3(WM * WN * 32), smem, a);
 }
 
 template <bool TA, bool TB, int VEC>

@@ -614,6 +614,7 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
     cgs2_fused_kernel<<<G, fthreads, smem, ctx->stream>>>(a);
     QTT_CUDA(cudaGetLastError());
   } else {
+    // (programmatic launch behind matvec_b was measured: no gain, 107.1 vs 107.2 ms per sweep)
     QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
   }
   ctx->launches++;

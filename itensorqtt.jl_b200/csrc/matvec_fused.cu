@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(WM* WN * 32) matvec_a_kernel(MvAArgs p) {
 
   // programmatic dependent launch: K_B's CTAs may become resident (and run their prologue) while this grid drains
   asm volatile("griddepcontrol.launch_dependents;\n" ::);
+  // ... and this grid is itself launched programmatically behind the producer of v
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
   for (int i = tid; i < 16 * WL * wr; i += NT) Ws[i] = p.W12[i];
 
   // ---- copy descriptors, computed once: global source (advanced per k-tile), shared destination of stage 0
@@ -435,8 +437,7 @@ void launch_mva(Ctx* ctx, const MvAArgs& a) {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((a.chil + 8 * MI * WM - 1) / (8 * MI * WM), (a.chir + 8 * WN - 1) / (8 * WN));
-  kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(a);
-  check_launch(ctx, "matvec_a");
+  launch_pdl(ctx, "matvec_a", kern, grid, dim3(WM * WN * 32), smem, a);
 }
 
 int g_mva_shape = -1;  // QTT_MVA_SHAPE: tuning override (0: 8 warps 32x16, 1: 4 warps 16x16, 2: 4 warps MI=2 32x16)

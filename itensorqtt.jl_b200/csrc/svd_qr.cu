@@ -46,6 +46,7 @@ struct QrCtl {
 // SE rows [0,q) = Z (zero padded to ldp), rows [q, q+p) = identity; norms[i] = |z_i|^2
 __global__ void qr_init_kernel(const double* __restrict__ M, int q, int p, int ldp, double* __restrict__ SE, double* __restrict__ norms,
                                int* __restrict__ rowstate, int* __restrict__ inpanel, QrCtl* ctl) {
+  dev::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int GW = (gridDim.x * blockDim.x) >> 5;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(double* __restrict__ 
                                                            const double* __restrict__ norms, int* __restrict__ rowstate,
                                                            int* __restrict__ inpanel, double* __restrict__ Vp,
                                                            double* __restrict__ taus, QrCtl* ctl) {
+  dev::pdl_wait();
   extern __shared__ double sm[];
   double* P = sm;                                      // [NB][ldp]
   double* nrm = sm + (size_t)nb * ldp;                 // [q] candidate norms (<0: not a candidate)
@@ -256,6 +258,7 @@ template <int NPL>
 __global__ void __launch_bounds__(PANEL_T) qr_apply_kernel(double* __restrict__ SE, int q, int p, int ldp, const int* __restrict__ rowstate,
                                                            const int* __restrict__ inpanel, const double* __restrict__ Vp,
                                                            const double* __restrict__ taus, double* __restrict__ norms, QrCtl* ctl) {
+  dev::pdl_wait();
   extern __shared__ double sm[];
   const int nbp = ctl->nbp;
   if (nbp == 0) return;
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(PANEL_T) qr_apply_generic_kernel(double* __res
                                                                    const int* __restrict__ rowstate, const int* __restrict__ inpanel,
                                                                    const double* __restrict__ Vp, const double* __restrict__ taus,
                                                                    double* __restrict__ norms, QrCtl* ctl) {
+  dev::pdl_wait();
   const int nbp = ctl->nbp;
   if (nbp == 0) return;
   const int serial = ctl->serial;
@@ -352,6 +356,7 @@ __global__ void __launch_bounds__(PANEL_T) qr_apply_generic_kernel(double* __res
 
 // Y[j][i] = SE[i][j] for j < r (tiled transpose); columns [q, qd) of Y are zero padding.
 __global__ void build_y_kernel(const double* __restrict__ SE, int q, int p, int ldp, int qd, int ldy, double* __restrict__ Y, const QrCtl* ctl) {
+  dev::pdl_wait();
   __shared__ double tile[32][33];
   const int r = ctl->r;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -770,6 +775,7 @@ void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
 __global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
                                    const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out,
                                    const double* __restrict__ SE, int q, int ldp) {
+  dev::pdl_wait();
   const int i = blockIdx.y;
   if (i >= k) return;
   const int src = perm[i];
@@ -828,8 +834,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     int rows = q + p;
     int grid = (rows + 7) / 8;
     if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
-    qr_init_kernel<<<grid, 256, 0, ctx->stream>>>(M, q, p, ldp, SE, norms, rowstate, inpanel, ctl);
-    check_launch(ctx, "qr_init");
+    launch_pdl(ctx, "qr_init", qr_init_kernel, dim3(grid), dim3(256), 0, M, q, p, ldp, SE, norms, rowstate, inpanel, ctl);
   }
   const int nb = panel_width(p);
   const size_t smem_panel = ((size_t)nb * ldp + q) * sizeof(double);
@@ -847,13 +852,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   for (int pn = 0; pn < npanels; ++pn) {
     // (a register-resident variant of this kernel -- rows in registers, reflector broadcast through shared memory -- was
     // measured slower in situ, 35 / 74 / 128 ms of split time per sweep against 32 / 69 / 127 ms, and was removed)
-    qr_panel_kernel<<<1, PANEL_T, smem_panel, ctx->stream>>>(SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel, Vp, taus, ctl);
-    check_launch(ctx, "qr_panel");
-    if (p <= 256) qr_apply_kernel<8><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
-    else if (p <= 512) qr_apply_kernel<16><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
-    else if (p <= 1024) qr_apply_kernel<32><<<agrid, PANEL_T, smem_apply, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
-    else qr_apply_generic_kernel<<<agrid, PANEL_T, 0, ctx->stream>>>(SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
-    check_launch(ctx, "qr_apply");
+    launch_pdl(ctx, "qr_panel", qr_panel_kernel, dim3(1), dim3(PANEL_T), smem_panel, SE, q, p, ldp, kmax, nb, zt * zt, norms, rowstate, inpanel,
+               Vp, taus, ctl);
+    if (p <= 256) launch_pdl(ctx, "qr_apply", qr_apply_kernel<8>, dim3(agrid), dim3(PANEL_T), smem_apply, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else if (p <= 512) launch_pdl(ctx, "qr_apply", qr_apply_kernel<16>, dim3(agrid), dim3(PANEL_T), smem_apply, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else if (p <= 1024) launch_pdl(ctx, "qr_apply", qr_apply_kernel<32>, dim3(agrid), dim3(PANEL_T), smem_apply, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
+    else launch_pdl(ctx, "qr_apply", qr_apply_generic_kernel, dim3(agrid), dim3(PANEL_T), 0, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
   }
   const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
   cudaEvent_t evq = nullptr, evj = nullptr;
@@ -864,8 +868,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   }
   {
     dim3 grid((q + p + 31) / 32, (kmax + 31) / 32);
-    build_y_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(SE, q, p, ldp, qd, ldy, Y, ctl);
-    check_launch(ctx, "build_y");
+    launch_pdl(ctx, "build_y", build_y_kernel, grid, dim3(32, 8), 0, SE, q, p, ldp, qd, ldy, Y, ctl);
   }
   QTT_CUDA(cudaMemsetAsync(ctx->d_sync + 8, 0, sizeof(unsigned) * (2 + 200), ctx->stream));
   JqArgs a;
@@ -938,8 +941,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   res.Wn = ctx->arena.alloc((size_t)res.k * p);
   res.Wni = nullptr;
   dim3 grid2((p + 255) / 256, res.k);
-  gather_rows_kernel<<<grid2, 256, 0, ctx->stream>>>(Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out, SE, q, ldp);
-  check_launch(ctx, "gather_rows");
+  launch_pdl(ctx, "gather_rows", gather_rows_kernel, grid2, dim3(256), 0, Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out, SE, q, ldp);
   return res;
 }
 
