@@ -6,6 +6,7 @@
 // and the skinny contractions over the MPO indices (K = 2w..4w, not tensor-core shaped) are fused into
 // one bandwidth-bound kernel each, which also performs the layout change the next GEMM needs.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include <cstdlib>
 
 namespace qtt {
@@ -14,6 +15,7 @@ namespace {
 // W12[(wl s1 s2)][(t1 t2 wr)] = sum_wm W1[wl][wm][s1][t1] W2[wm][wr][s2][t2]
 __global__ void build_w12_kernel(const double* __restrict__ W1, const double* __restrict__ W2, double* __restrict__ W12, int wl,
                                  int wm, int wr) {
+  dev::pdl_wait();
   int total = 16 * wl * wr;
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
     int col = o % (4 * wr), row = o / (4 * wr);
@@ -57,6 +59,7 @@ __global__ void apply_w12_kernel(const double* __restrict__ T1, const double* __
 // generic (any wl): no register caching
 __global__ void apply_w12_generic_kernel(const double* __restrict__ T1, const double* __restrict__ W12, double* __restrict__ T2,
                                          int chil, int chir, int wl, int wr) {
+  dev::pdl_wait();
   const int nin = 4 * wl, nout = 4 * wr;
   const int ap = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,6 +76,7 @@ __global__ void apply_w12_generic_kernel(const double* __restrict__ T1, const do
 
 // out[i] = sum_b P[b][i]
 __global__ void sum_partials_kernel(const double* __restrict__ P, double* __restrict__ out, long n, int nb) {
+  dev::pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     double acc = P[i];
     for (int b = 1; b < nb; ++b) acc += P[(long)b * n + i];
@@ -83,6 +87,7 @@ __global__ void sum_partials_kernel(const double* __restrict__ P, double* __rest
 // U[w2][a'][t][b] = sum_{w, s} W[w][w2][s][t] T[w][a'][s][b]      (left environment, middle step)
 __global__ void env_left_mid_kernel(const double* __restrict__ T, const double* __restrict__ W, double* __restrict__ U, int chia,
                                     int chib, int w, int w2) {
+  dev::pdl_wait();
   extern __shared__ double ws[];
   for (int i = threadIdx.x; i < w * w2 * 4; i += blockDim.x) ws[i] = W[i];
   __syncthreads();
@@ -106,6 +111,7 @@ __global__ void env_left_mid_kernel(const double* __restrict__ T, const double* 
 // U[w][s][c][a'] = sum_{w2, t} W[w][w2][s][t] T[w2][c][a'][t]      (right environment, middle step)
 __global__ void env_right_mid_kernel(const double* __restrict__ T, const double* __restrict__ W, double* __restrict__ U, int chic,
                                      int chia, int w, int w2) {
+  dev::pdl_wait();
   extern __shared__ double ws[];
   for (int i = threadIdx.x; i < w * w2 * 4; i += blockDim.x) ws[i] = W[i];
   __syncthreads();
@@ -130,8 +136,7 @@ __global__ void env_right_mid_kernel(const double* __restrict__ T, const double*
 
 void build_w12(Ctx* ctx, const double* W1, const double* W2, double* W12, int wl, int wm, int wr) {
   int total = 16 * wl * wr;
-  build_w12_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(W1, W2, W12, wl, wm, wr);
-  check_launch(ctx, "build_w12");
+  launch_pdl(ctx, "build_w12", build_w12_kernel, dim3((total + 127) / 128), dim3(128), 0, W1, W2, W12, wl, wm, wr);
 }
 
 size_t matvec2_scratch(int chil, int chir, int wl, int wr) {
@@ -165,8 +170,7 @@ void matvec2(Ctx* ctx, const double* L, const double* W12, const double* R, cons
     size_t smem = (size_t)16 * wl * wr * sizeof(double);
     if (wl <= 4) apply_w12_kernel<4><<<grid, threads, smem, ctx->stream>>>(T1, W12, T2, chil, chir, wl, wr);
     else if (wl <= 8 && smem <= 48 * 1024) apply_w12_kernel<8><<<grid, threads, smem, ctx->stream>>>(T1, W12, T2, chil, chir, wl, wr);
-    else apply_w12_generic_kernel<<<grid, threads, 0, ctx->stream>>>(T1, W12, T2, chil, chir, wl, wr);
-    check_launch(ctx, "apply_w12");
+    else launch_pdl(ctx, "apply_w12", apply_w12_generic_kernel, dim3(grid), dim3(threads), 0, T1, W12, T2, chil, chir, wl, wr);
   }
   // stage 4: out[(a' t12)][c'] = T2[(a' t12)][(wr c)] . R[(wr c)][c'].  The output is small (4 chil x chir)
   // and K is long (wr chir): when it cannot fill the SMs it is split over wr into partial products.
@@ -189,8 +193,7 @@ void matvec2(Ctx* ctx, const double* L, const double* W12, const double* R, cons
     gemm(ctx, g4);
     long nblk = ((long)base + 255) / 256;
     if (nblk > 8L * ctx->sms) nblk = 8L * ctx->sms;
-    sum_partials_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(P, out, (long)base, wr);
-    check_launch(ctx, "sum_partials");
+    launch_pdl(ctx, "sum_partials", sum_partials_kernel, dim3((unsigned)nblk), dim3(256), 0, P, out, (long)base, wr);
   }
 }
 
@@ -212,8 +215,7 @@ void env_left(Ctx* ctx, const double* L, const double* x, const double* W, const
   {
     const int threads = chib >= 128 ? 128 : (chib >= 64 ? 64 : 32);
     dim3 grid((chib + threads - 1) / threads, chia_y);
-    env_left_mid_kernel<<<grid, threads, (size_t)w * w2 * 4 * sizeof(double), ctx->stream>>>(T, W, U, chia_y, chib, w, w2);
-    check_launch(ctx, "env_left_mid");
+    launch_pdl(ctx, "env_left_mid", env_left_mid_kernel, dim3(grid), dim3(threads), (size_t)w * w2 * 4 * sizeof(double), T, W, U, chia_y, chib, w, w2);
   }
   GemmDesc g3;
   g3.A = y; g3.B = U; g3.C = Lnew;
@@ -239,8 +241,7 @@ void env_right(Ctx* ctx, const double* R, const double* x, const double* W, cons
   {
     const int threads = chia_y >= 128 ? 128 : (chia_y >= 64 ? 64 : 32);
     dim3 grid((chia_y + threads - 1) / threads, chic);
-    env_right_mid_kernel<<<grid, threads, (size_t)w * w2 * 4 * sizeof(double), ctx->stream>>>(T, W, U, chic, chia_y, w, w2);
-    check_launch(ctx, "env_right_mid");
+    launch_pdl(ctx, "env_right_mid", env_right_mid_kernel, dim3(grid), dim3(threads), (size_t)w * w2 * 4 * sizeof(double), T, W, U, chic, chia_y, w, w2);
   }
   GemmDesc g3;
   g3.A = x; g3.B = U; g3.C = Rnew;

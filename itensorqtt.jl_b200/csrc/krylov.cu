@@ -23,6 +23,7 @@ constexpr int NV = 32;
 __global__ void __launch_bounds__(KT) dots_kernel(const double* __restrict__ V, int nvec, size_t len, const double* __restrict__ w,
                                                   double* __restrict__ partial, double* __restrict__ h, unsigned int* counter,
                                                   int accumulate) {
+  dev::pdl_wait();
   __shared__ double red[KT / 32][NV + 1];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(KT) dots_kernel(const double* __restrict__ V, 
 __global__ void __launch_bounds__(KT) axpys_kernel(const double* __restrict__ V, int nvec, size_t len, const double* __restrict__ h,
                                                    double* __restrict__ w, double sign, double* __restrict__ partial,
                                                    double* __restrict__ nrm2sq_out, unsigned int* counter) {
+  dev::pdl_wait();
   extern __shared__ double hs[];
   __shared__ double red[KT / 32];
   __shared__ bool is_last;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(KT) axpys_kernel(const double* __restrict__ V,
 // out[e] = w[e] / d  with d = *denom (or sqrt(*denom))
 __global__ void __launch_bounds__(KT) scale_to_kernel(const double* __restrict__ w, size_t len, const double* __restrict__ denom,
                                                       int sqrt_denom, double* __restrict__ out, const double* __restrict__ done) {
+  dev::pdl_wait();
   double d = *denom;
   if (sqrt_denom) d = sqrt(d);
   // once the Krylov space is exhausted / converged (device flag), later basis vectors are written as zeros so that
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(KT) scale_to_kernel(const double* __restrict__
 __global__ void __launch_bounds__(KT) axpby_kernel(size_t len, double a, const double* __restrict__ x, double b,
                                                    const double* __restrict__ y, double c, const double* __restrict__ z,
                                                    double* __restrict__ out) {
+  dev::pdl_wait();
   for (size_t e = (size_t)blockIdx.x * KT + threadIdx.x; e < len; e += (size_t)gridDim.x * KT) {
     double v = 0.0;
     if (x) v += a * x[e];
@@ -496,8 +500,7 @@ static void dots_impl(Ctx* ctx, const double* V, int nvec, size_t len, const dou
   for (int i0 = 0; i0 < nvec; i0 += NV) {
     int nv = nvec - i0 < NV ? nvec - i0 : NV;
     double* part = ctx->partial((size_t)g * nv);
-    dots_kernel<<<g, KT, 0, ctx->stream>>>(V + (size_t)i0 * len, nv, len, w, part, h + i0, ctx->d_sync + 0, accumulate);
-    check_launch(ctx, "kry_dots");
+    launch_pdl(ctx, "kry_dots", dots_kernel, dim3(g), dim3(KT), 0, V + (size_t)i0 * len, nv, len, w, part, h + i0, ctx->d_sync + 0, accumulate);
   }
 }
 
@@ -514,9 +517,8 @@ void kry_dots_acc(Ctx* ctx, const double* V, int nvec, size_t len, const double*
 void kry_axpys_nrm(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign, double* nrm2sq_out) {
   unsigned g = grid_for(ctx, len, CHUNK);
   double* part = ctx->partial(g);
-  axpys_kernel<<<g, KT, (size_t)(nvec > 0 ? nvec : 1) * sizeof(double), ctx->stream>>>(V, nvec, len, h, w, sign, part, nrm2sq_out,
+  launch_pdl(ctx, "kry_axpys", axpys_kernel, dim3(g), dim3(KT), (size_t)(nvec > 0 ? nvec : 1) * sizeof(double), V, nvec, len, h, w, sign, part, nrm2sq_out,
                                                                                       ctx->d_sync + 1);
-  check_launch(ctx, "kry_axpys");
 }
 
 void kry_axpys(Ctx* ctx, const double* V, int nvec, size_t len, const double* h, double* w, double sign) {
@@ -528,20 +530,17 @@ void kry_nrm2sq(Ctx* ctx, const double* w, size_t len, double* out) {
   // ||w||^2 = w . w through the dot kernel (one "basis vector" = w itself)
   unsigned g = grid_for(ctx, len, CHUNK);
   double* part = ctx->partial(g);
-  dots_kernel<<<g, KT, 0, ctx->stream>>>(w, 1, len, w, part, out, ctx->d_sync + 0, 0);
-  check_launch(ctx, "kry_nrm2sq");
+  launch_pdl(ctx, "kry_nrm2sq", dots_kernel, dim3(g), dim3(KT), 0, w, 1, len, w, part, out, ctx->d_sync + 0, 0);
 }
 
 void kry_scale_to(Ctx* ctx, const double* w, size_t len, const double* denom_dev, bool sqrt_denom, double* out, const double* done_dev) {
   unsigned g = grid_for(ctx, len, KT);
-  scale_to_kernel<<<g, KT, 0, ctx->stream>>>(w, len, denom_dev, sqrt_denom ? 1 : 0, out, done_dev);
-  check_launch(ctx, "kry_scale_to");
+  launch_pdl(ctx, "kry_scale_to", scale_to_kernel, dim3(g), dim3(KT), 0, w, len, denom_dev, sqrt_denom ? 1 : 0, out, done_dev);
 }
 
 void kry_axpby(Ctx* ctx, size_t len, double a, const double* x, double b, const double* y, double c, const double* z, double* out) {
   unsigned g = grid_for(ctx, len, KT);
-  axpby_kernel<<<g, KT, 0, ctx->stream>>>(len, a, x, b, y, c, z, out);
-  check_launch(ctx, "kry_axpby");
+  launch_pdl(ctx, "kry_axpby", axpby_kernel, dim3(g), dim3(KT), 0, len, a, x, b, y, c, z, out);
 }
 
 }  // namespace qtt

@@ -3,6 +3,7 @@
 // (input-fastest dim, output-fastest dim): reads are coalesced along the input's fastest index,
 // writes along the output's fastest index, the remaining dims are enumerated by blockIdx.z.
 #include "common.cuh"
+#include "device_utils.cuh"
 
 namespace qtt {
 namespace {
@@ -20,6 +21,7 @@ struct PermArgs {
 };
 
 __global__ void permute_tiled_kernel(const double* __restrict__ in, double* __restrict__ out, PermArgs a) {
+  dev::pdl_wait();
   __shared__ double tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long x0 = (long)blockIdx.x * 32, y0 = (long)blockIdx.y * 32;
@@ -51,6 +53,7 @@ __global__ void permute_tiled_kernel(const double* __restrict__ in, double* __re
 // fastest dims coincide: plain gather with coalesced reads and writes
 __global__ void permute_rows_kernel(const double* __restrict__ in, double* __restrict__ out, PermArgs a, int perm0, int perm1,
                                     int perm2, int perm3, int perm4, int perm5) {
+  dev::pdl_wait();
   const int perm[MAXD] = {perm0, perm1, perm2, perm3, perm4, perm5};
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < a.total; o += (long)gridDim.x * blockDim.x) {
     long r = o, off = 0;
@@ -110,8 +113,7 @@ void permute(Ctx* ctx, const double* in, double* out, int nd, const int64_t* dim
     for (int k = 0; k < nd; ++k) pp[k] = perm[k];
     long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    permute_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, a, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5]);
-    check_launch(ctx, "permute_rows");
+    launch_pdl(ctx, "permute_rows", permute_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, in, out, a, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5]);
     return;
   }
   a.dx = nd - 1;
@@ -119,8 +121,7 @@ void permute(Ctx* ctx, const double* in, double* out, int nd, const int64_t* dim
   a.rest_count = total / (a.dim[a.dx] * a.dim[a.dy]);
   dim3 grid((unsigned)((a.dim[a.dx] + 31) / 32), (unsigned)((a.dim[a.dy] + 31) / 32),
             (unsigned)(a.rest_count > 32768 ? 32768 : a.rest_count));
-  permute_tiled_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(in, out, a);
-  check_launch(ctx, "permute_tiled");
+  launch_pdl(ctx, "permute_tiled", permute_tiled_kernel, dim3(grid), dim3(dim3(32, 8)), 0, in, out, a);
 }
 
 void deinterleave(Ctx* ctx, const double* in, double* re, double* im, size_t n) {

@@ -12,6 +12,7 @@
 // GMRES scalars (Hessenberg column, Givens rotations, residual estimate, convergence flag) live in device memory and
 // are advanced by a one-thread kernel; the host polls a pinned, device-written flag to stop enqueuing early.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include "krylov_scalars.cuh"
 #include <chrono>
 #include <functional>
@@ -27,12 +28,14 @@ using namespace kscal;
 int g_trace_sweeps = 0;  // sweeps completed in this process (QTT_DUMP addresses a sweep by this count)
 
 __global__ void gmres_update_kernel(double* S, int k, double a0, double a1, double tol, int ld, volatile double* hstat) {
+  dev::pdl_wait();
   gmres_step_scalars(S, k, a0, a1, tol, ld, hstat);
 }
 
 // Back substitution R yk = y, and the coefficients of the restart residual r = y[k] * [V, w/nres] (G_1^H ... G_k^H e_{k+1}).
 // single-thread back substitution on a shared-memory copy of the scalar block (global-memory latency made it 49 us)
 __global__ void __launch_bounds__(256) gmres_solve_kernel(double* S, int k_or_neg_kd, int ld) {
+  dev::pdl_wait();
   extern __shared__ double Ss[];
   for (int i = threadIdx.x; i < OFF_END; i += blockDim.x) Ss[i] = S[i];
   __syncthreads();
@@ -42,11 +45,13 @@ __global__ void __launch_bounds__(256) gmres_solve_kernel(double* S, int k_or_ne
 }
 
 __global__ void set_scalars_kernel(double* p, int n, double v) {
+  dev::pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 
 __global__ void scale_inplace_kernel(double* w, size_t len, const double* nrm2sq) {
+  dev::pdl_wait();
   double inv = rsqrt(*nrm2sq);
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (size_t)gridDim.x * blockDim.x) w[e] *= inv;
 }
@@ -96,8 +101,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
   int numiter = 0;
   while (numiter < maxiter) {
     numiter++;
-    set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
-    check_launch(ctx, "set_scalars");
+    launch_pdl(ctx, "set_scalars", set_scalars_kernel, dim3(1), dim3(32), 0, S + S_DONE, 2, 0.0);
     kry_scale_to(ctx, ws.r, len, S + S_R0N2, true, vec(0));
     if (!fixed) hstat[H_DONE] = 0.0;
     int k;
@@ -115,8 +119,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
         kry_axpys(ctx, ws.V, k, len, S + OFF_H1, ws.w, -1.0);
         kry_dots(ctx, ws.V, k, len, ws.w, S + OFF_H2);
         kry_axpys_nrm(ctx, ws.V, k, len, S + OFF_H2, ws.w, -1.0, S + S_NRES2);
-        gmres_update_kernel<<<1, 1, 0, ctx->stream>>>(S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
-        check_launch(ctx, "gmres_update");
+        launch_pdl(ctx, "gmres_update", gmres_update_kernel, dim3(1), dim3(1), 0, S, k, a0, a1, fixed ? -1.0 : tol, 64, fixed ? nullptr : ctx->h_scal);
         kry_scale_to(ctx, ws.w, len, S + S_NRES2, true, vec(k), S + S_DONE);
       }
       if (!fixed && hstat[H_DONE] != 0.0) break;
@@ -131,8 +134,7 @@ void gmres_local(Ctx* ctx, const MatvecFn& mv, const double* beff, double* x, si
     }
     // fixed mode: the device-side step count (S_K < kd after an early breakdown) is used by the kernel itself; the
     // coefficients beyond it are zero and the corresponding basis vectors were written as zeros.
-    gmres_solve_kernel<<<1, 256, OFF_END * sizeof(double), ctx->stream>>>(S, fixed ? -kd : kfin, 64);
-    check_launch(ctx, "gmres_solve");
+    launch_pdl(ctx, "gmres_solve", gmres_solve_kernel, dim3(1), dim3(256), OFF_END * sizeof(double), S, fixed ? -kd : kfin, 64);
     kry_axpys(ctx, ws.V, kfin, len, S + OFF_YK, x, 1.0);
     if (fixed) return;
     if (beta > tol) {
@@ -247,8 +249,7 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
     int kused = kd;
     bool early = false;
     kry_nrm2sq(ctx, x, len, S + S_R0N2);
-    set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(S + S_DONE, 2, 0.0);
-    check_launch(ctx, "set_scalars");
+    launch_pdl(ctx, "set_scalars", set_scalars_kernel, dim3(1), dim3(32), 0, S + S_DONE, 2, 0.0);
     kry_scale_to(ctx, x, len, S + S_R0N2, true, vec(0));
     QTT_CUDA(cudaMemsetAsync(S + OFF_R, 0, sizeof(double) * 64 * 64, ctx->stream));
     for (int k = 1; k <= kd; ++k) {
@@ -340,8 +341,7 @@ void project_rhs(Ctx* ctx, const double* Lb, const double* b1, const double* b2,
 
 void set_one(Ctx* ctx, DBuf& b) {
   dbuf_reserve(b, 2);
-  set_scalars_kernel<<<1, 32, 0, ctx->stream>>>(b.p, 1, 1.0);
-  check_launch(ctx, "set_one");
+  launch_pdl(ctx, "set_one", set_scalars_kernel, dim3(1), dim3(32), 0, b.p, 1, 1.0);
 }
 
 double matvec_flops(double chil, double chir, double wl, double wm, double wr) {
@@ -587,8 +587,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
             kry_nrm2sq(ctx, phi, len, ctx->d_scal + S_TMP);
             long nb = (long)((len + 255) / 256);
             if (nb > 4L * ctx->sms) nb = 4L * ctx->sms;
-            scale_inplace_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(phi, len, ctx->d_scal + S_TMP);
-            check_launch(ctx, "scale_inplace");
+            launch_pdl(ctx, "scale_inplace", scale_inplace_kernel, dim3((unsigned)nb), dim3(256), 0, phi, len, ctx->d_scal + S_TMP);
           }
           int kcap = 2 * chil < 2 * chir ? 2 * chil : 2 * chir;
           if (maxdim > 0 && maxdim < kcap) kcap = maxdim;
