@@ -158,6 +158,21 @@ QTT_API int qtt_apply(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* psi, double
 QTT_API int qtt_vec_to_mps(qtt_ctx* ctx, const double* v, int32_t n, int32_t on_device, double cutoff, int32_t maxdim, int32_t mindim,
                            qtt_mps** out, double* maxtruncerr);
 
+/* ---- sum, dense expansion, point sampling ------------------------------------------------------
+ * out = alpha x + beta y, truncated: ITensorMPS `+(x, y; cutoff, maxdim)` as called at reference
+ * src/fourier_interpolation.jl:8 (also src/function_to_mps.jl:123, src/laplacian.jl:106).  The direct sum is assembled on
+ * the device and compressed by the density-matrix pass of `qtt_apply` (NDTensors.truncate! rule); x, y real or complex. */
+QTT_API int qtt_mps_add(qtt_ctx* ctx, const qtt_mps* x, const qtt_mps* y, double alpha, double beta, double cutoff, int32_t maxdim,
+                        int32_t mindim, qtt_mps** out);
+/* `mps_to_discrete_function(psi)` (reference src/function_to_mps.jl:140-145, one dimension): all 2^n values, value j at the
+ * bits of j with site 1 = most significant bit (the inverse of qtt_vec_to_mps).  out: 2^n doubles (f64 chain) or 2^n
+ * interleaved complex (c128 chain); host memory (on_device = 0) or device memory on ctx's GPU (on_device = 1). */
+QTT_API int qtt_mps_to_vec(qtt_ctx* ctx, const qtt_mps* x, void* out, int32_t on_device);
+/* Values at `count` grid indices: `project_bits(psi, bits)` with every site projected (reference src/project_bits.jl:1-15,
+ * scalar return :11-13), batched; 0 <= idx[i] < 2^n, bits of idx[i] with site 1 = most significant bit.  idx and out are
+ * host arrays; out: count doubles or count interleaved complex. */
+QTT_API int qtt_mps_sample(qtt_ctx* ctx, const qtt_mps* x, const int64_t* idx, int64_t count, void* out);
+
 /* ---- metrics (reference src/mps_utils.jl:109-132) ------------------------------------------- */
 /* inner(x, y) = <x|y>; out2 = {re, im} */
 QTT_API int qtt_inner(qtt_ctx* ctx, const qtt_mps* x, const qtt_mps* y, double* out2);

@@ -71,6 +71,9 @@ EXPORTED_SYMBOLS = {
     "qtt_set_profiling": (C.c_int, [_vp, C.c_int]),
     "qtt_apply": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int32, C.c_int32, _vpp]),
     "qtt_vec_to_mps": (C.c_int, [_vp, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _vpp, _dp]),
+    "qtt_mps_add": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, _vpp]),
+    "qtt_mps_to_vec": (C.c_int, [_vp, _vp, C.c_void_p, C.c_int32]),
+    "qtt_mps_sample": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_void_p]),
     "qtt_inner": (C.c_int, [_vp, _vp, _vp, _dp]),
     "qtt_residual": (C.c_int, [_vp, _vp, _vp, _vp, _dp, _dp]),
     "qtt_matvec2": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

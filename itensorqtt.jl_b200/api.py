@@ -11,7 +11,7 @@ from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dpt
 from .chains import DeviceMPS, DeviceMPO
 
 __all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "vec_to_mps", "function_to_mps", "apply_dft_mpo", "apply_idft_mpo",
-           "fourier_interpolation", "repeat_function", "apply", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
+           "fourier_interpolation", "repeat_function", "apply", "add", "mps_to_vec", "sample", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
            "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN"]
 
@@ -192,6 +192,61 @@ def function_to_mps(f, n, xstart, xstop, *, cutoff=1e-15, alg="factorize", **kwa
         raise NotImplementedError('only alg="factorize" runs on the device; the polynomial construction (:88-133) is host-side')
     from .operators import qtt_xrange
     return vec_to_mps(f(qtt_xrange(n, xstart, xstop)), cutoff=cutoff, **kwargs)
+
+
+def add(x, y, *, alpha=1.0, beta=1.0, cutoff=1e-15, maxdim=None, mindim=1, ctx=None, on_device=False):
+    """`+(x, y; cutoff, maxdim)` of ITensorMPS (reference call sites src/fourier_interpolation.jl:8, src/function_to_mps.jl:123),
+    generalised to alpha x + beta y: the direct sum is assembled and truncated on the GPU (`qtt_mps_add`)."""
+    ctx = ctx or default_context()
+    dx, fx = _as_dev_mps(x, ctx)
+    dy, fy = _as_dev_mps(y, ctx)
+    out = C.c_void_p()
+    try:
+        check(ctx.handle, lib.qtt_mps_add(ctx.handle, dx.handle, dy.handle, float(alpha), float(beta), float(cutoff), int(maxdim or 0),
+                                          int(mindim), C.byref(out)))
+    finally:
+        if fx:
+            dx.free()
+        if fy:
+            dy.free()
+    res = DeviceMPS(ctx=ctx, _handle=out)
+    if on_device:
+        return res
+    cores = res.download()
+    res.free()
+    return cores
+
+
+def mps_to_vec(psi, ctx=None):
+    """`mps_to_discrete_function(psi)` (reference src/function_to_mps.jl:136-145, one dimension) on the GPU -- the inverse of
+    `vec_to_mps`: the 2^n grid values, site 1 = most significant bit, expanded by `qtt_mps_to_vec` and returned as a host array.
+    (`operators.mps_to_discrete_function` is the host-side restatement used for operand specs.)"""
+    ctx = ctx or default_context()
+    dp, fp = _as_dev_mps(psi, ctx)
+    try:
+        n = len(dp)
+        out = np.empty(1 << n, dtype=np.complex128 if dp.is_complex else np.float64)
+        check(ctx.handle, lib.qtt_mps_to_vec(ctx.handle, dp.handle, C.c_void_p(out.ctypes.data), 0))
+    finally:
+        if fp:
+            dp.free()
+    return out
+
+
+def sample(psi, idx, ctx=None):
+    """Values of the QTT at the grid indices `idx` (0-based, site 1 = most significant bit): `project_bits(psi, bits)` with every
+    site projected (reference src/project_bits.jl:1-15, scalar return :11-13), batched on the GPU (`qtt_mps_sample`)."""
+    ctx = ctx or default_context()
+    ii = np.ascontiguousarray(np.asarray(idx, dtype=np.int64).reshape(-1))
+    dp, fp = _as_dev_mps(psi, ctx)
+    try:
+        out = np.empty(ii.size, dtype=np.complex128 if dp.is_complex else np.float64)
+        check(ctx.handle, lib.qtt_mps_sample(ctx.handle, dp.handle, ii.ctypes.data_as(C.POINTER(C.c_int64)), int(ii.size),
+                                             C.c_void_p(out.ctypes.data)))
+    finally:
+        if fp:
+            dp.free()
+    return out.reshape(np.shape(idx))
 
 
 def inner(x, y, ctx=None):

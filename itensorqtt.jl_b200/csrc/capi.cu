@@ -7,9 +7,6 @@
 
 namespace qtt {
 void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_sweep_params& P, qtt_sweep_info* infos);
-void apply_mpo_mps(Ctx* ctx, const Mpo& A, const Mps& psi, double cutoff, int maxdim, int mindim, Mps& out);
-void mps_inner(Ctx* ctx, const Mps& x, const Mps& y, double* out2);
-void mps_residual(Ctx* ctx, const Mpo& A, const Mps& x, const Mps& b, double* sq, double* sqn);
 
 static std::string g_error;
 static std::mutex g_mutex;
@@ -496,6 +493,91 @@ int qtt_vec_to_mps(qtt_ctx* ctx, const double* v, int32_t n, int32_t on_device, 
   if (staged) pool_free(staged, ctx->stream);
   if (total >= ((size_t)1 << 26)) pool_trim();  // do not keep multi-GB staging buffers cached
   *out = m;
+  QTT_CATCH(ctx)
+}
+
+// ---- sum, dense expansion, point sampling ------------------------------------------------------
+int qtt_mps_add(qtt_ctx* ctx, const qtt_mps* x, const qtt_mps* y, double alpha, double beta, double cutoff, int32_t maxdim, int32_t mindim,
+                qtt_mps** out) {
+  QTT_TRY(ctx)
+  QTT_REQUIRE(ctx && x && y && out, "qtt_mps_add: null argument");
+  QTT_REQUIRE(x->ctx == ctx && y->ctx == ctx, "chains belong to a different context");
+  QTT_CUDA(cudaSetDevice(ctx->device));
+  qtt_mps* m = new qtt_mps();
+  m->ctx = ctx;
+  try {
+    mps_add(ctx, *x, *y, alpha, beta, cutoff, maxdim, mindim, *m);
+  } catch (...) { delete m; throw; }
+  *out = m;
+  QTT_CATCH(ctx)
+}
+
+int qtt_mps_to_vec(qtt_ctx* ctx, const qtt_mps* x, void* out, int32_t on_device) {
+  QTT_TRY(ctx)
+  QTT_REQUIRE(ctx && x && out, "qtt_mps_to_vec: null argument");
+  QTT_REQUIRE(x->ctx == ctx, "chain belongs to a different context");
+  QTT_REQUIRE(x->n >= 1 && x->n <= 34, "qtt_mps_to_vec: n = %d out of range [1, 34]", x->n);
+  QTT_CUDA(cudaSetDevice(ctx->device));
+  {
+    cudaPointerAttributes pa;
+    const cudaError_t e = cudaPointerGetAttributes(&pa, out);
+    cudaGetLastError();
+    const bool is_dev = (e == cudaSuccess) && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    if (on_device) {
+      QTT_REQUIRE(is_dev, "qtt_mps_to_vec: on_device = 1 but out is not a device pointer");
+      QTT_REQUIRE(pa.type == cudaMemoryTypeManaged || pa.device == ctx->device, "qtt_mps_to_vec: out lives on device %d, the context on device %d",
+                  pa.device, ctx->device);
+    } else {
+      QTT_REQUIRE(!(e == cudaSuccess && pa.type == cudaMemoryTypeDevice), "qtt_mps_to_vec: on_device = 0 but out is a device pointer");
+    }
+  }
+  const size_t total = (size_t)1 << x->n;
+  const bool cplx = x->dtype == QTT_C128;
+  Scratch sc;
+  if (!cplx) {
+    double* dst = on_device ? static_cast<double*>(out) : sc.get(total);
+    mps_to_vec(ctx, *x, dst, nullptr);
+    if (!on_device) QTT_CUDA(cudaMemcpyAsync(out, dst, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    double* re = sc.get(total);
+    double* im = sc.get(total);
+    mps_to_vec(ctx, *x, re, im);
+    double* il = on_device ? static_cast<double*>(out) : sc.get(2 * total);
+    interleave(ctx, re, im, il, total);
+    if (!on_device) QTT_CUDA(cudaMemcpyAsync(out, il, 2 * total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (total >= ((size_t)1 << 26)) pool_trim();
+  QTT_CATCH(ctx)
+}
+
+int qtt_mps_sample(qtt_ctx* ctx, const qtt_mps* x, const int64_t* idx, int64_t count, void* out) {
+  QTT_TRY(ctx)
+  QTT_REQUIRE(ctx && x && (count == 0 || (idx && out)), "qtt_mps_sample: null argument");
+  QTT_REQUIRE(x->ctx == ctx, "chain belongs to a different context");
+  QTT_REQUIRE(count >= 0, "qtt_mps_sample: negative count");
+  QTT_CUDA(cudaSetDevice(ctx->device));
+  if (count > 0) {
+    const int64_t limit = x->n >= 63 ? INT64_MAX : ((int64_t)1 << x->n);
+    for (int64_t i = 0; i < count; ++i)
+      QTT_REQUIRE(idx[i] >= 0 && idx[i] < limit, "qtt_mps_sample: grid index %lld (entry %lld) outside [0, 2^%d)", (long long)idx[i],
+                  (long long)i, x->n);
+    const bool cplx = x->dtype == QTT_C128;
+    Scratch sc;
+    static_assert(sizeof(int64_t) == sizeof(double), "index staging reuses the double pool");
+    int64_t* d_idx = reinterpret_cast<int64_t*>(sc.get((size_t)count));
+    QTT_CUDA(cudaMemcpyAsync(d_idx, idx, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    double* d_out = sc.get((size_t)count * (cplx ? 2 : 1));
+    mps_sample(ctx, *x, d_idx, count, d_out);
+    if (!cplx) {
+      QTT_CUDA(cudaMemcpyAsync(out, d_out, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      double* il = sc.get((size_t)2 * count);
+      interleave(ctx, d_out, d_out + count, il, (size_t)count);
+      QTT_CUDA(cudaMemcpyAsync(out, il, (size_t)2 * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   QTT_CATCH(ctx)
 }
 

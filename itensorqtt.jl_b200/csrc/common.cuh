@@ -263,6 +263,16 @@ SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, d
 // ------------------------------------------------------------------ TT-SVD of a sample vector (ttsvd.cu)
 void vec_to_mps(Ctx* ctx, const double* v_dev, int n, double cutoff, int maxdim, int mindim, Mps& out, double* maxerr_out);
 
+// ------------------------------------------------------------------ apply / metrics (apply.cu)
+void apply_mpo_mps(Ctx* ctx, const Mpo& A, const Mps& psi, double cutoff, int maxdim, int mindim, Mps& out);
+void mps_inner(Ctx* ctx, const Mps& x, const Mps& y, double* out2);
+void mps_residual(Ctx* ctx, const Mpo& A, const Mps& x, const Mps& b, double* sq, double* sqn);
+
+// ------------------------------------------------------------------ sum, dense expansion, point sampling (mps_algebra.cu)
+void mps_add(Ctx* ctx, const Mps& x, const Mps& y, double alpha, double beta, double cutoff, int maxdim, int mindim, Mps& out);
+void mps_to_vec(Ctx* ctx, const Mps& x, double* out_re_dev, double* out_im_dev /* null for a real chain */);
+void mps_sample(Ctx* ctx, const Mps& x, const int64_t* idx_dev, int64_t count, double* out_dev /* [count] re (+ [count] im) */);
+
 }  // namespace qtt
 
 struct qtt_ctx : qtt::Ctx {};

@@ -292,6 +292,48 @@ function apply_idft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
   return MPS(reverse([phi[j] for j in 1:length(phi)]))
 end
 
+# `+(x, y; cutoff, maxdim)` of ITensorMPS (reference src/fourier_interpolation.jl:8, src/function_to_mps.jl:123) on the device:
+# the direct sum is assembled in HBM and compressed by the density-matrix pass of `qtt_apply`
+function add_mps(x::MPS, y::MPS; alpha=1.0, beta=1.0, cutoff=1e-15, maxdim=0, mindim=1, ctx::Context=context())
+  hx = upload(ctx, x); hy = upload(ctx, y)
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  try
+    check(ctx, ccall((:qtt_mps_add, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                     ctx.handle, hx, hy, alpha, beta, cutoff, maxdim, mindim, out))
+    return download(ctx, out[], siteinds(x))
+  finally
+    out[] != C_NULL && free_mps(out[]); free_mps(hy); free_mps(hx)
+  end
+end
+
+# `mps_to_discrete_function(psi)` (reference src/function_to_mps.jl:140-145, one dimension): expanded on the device
+function mps_to_discrete_function(psi::MPS; ctx::Context=context())
+  hp = upload(ctx, psi)
+  T = any(j -> eltype(psi[j]) <: Complex, 1:length(psi)) ? ComplexF64 : Float64
+  out = Vector{T}(undef, 2^length(psi))
+  try
+    GC.@preserve out check(ctx, ccall((:qtt_mps_to_vec, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32), ctx.handle, hp, pointer(out), 0))
+    return out
+  finally
+    free_mps(hp)
+  end
+end
+
+# values at 0-based grid indices: `project_bits(psi, bits)` with every site projected (reference src/project_bits.jl:1-15), batched
+function sample_values(psi::MPS, idx::AbstractVector{<:Integer}; ctx::Context=context())
+  hp = upload(ctx, psi)
+  T = any(j -> eltype(psi[j]) <: Complex, 1:length(psi)) ? ComplexF64 : Float64
+  ii = Vector{Int64}(idx)
+  out = Vector{T}(undef, length(ii))
+  try
+    GC.@preserve ii out check(ctx, ccall((:qtt_mps_sample, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}),
+                                         ctx.handle, hp, pointer(ii), length(ii), pointer(out)))
+    return out
+  finally
+    free_mps(hp)
+  end
+end
+
 # residual metric of reference src/mps_utils.jl:109-116
 """
     vec_to_mps(v::AbstractVector, s::Vector{<:Index}; cutoff=1e-15, maxdim=0, mindim=1)
