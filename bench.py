@@ -57,7 +57,7 @@ def workload(rank=0, n=N_BITS, chi=CHI, nk=NK):
     # independent instances at N > 1: wavenumber k_i = 2 pi (2^nk + rank)  (SURVEY.md 8d cfg 5 recipe)
     lam = -((2 * np.pi * (2.0 ** nk + rank) / 2.0 ** n) ** 2)
     b = q.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
-    x0 = q.random_mps(n, chi, 2 + rank)
+    x0 = q.random_mps(n, chi, 2)   # a wavenumber sweep starts every k from the same guess: equal work per rank by construction
     return A, b, x0, lam
 
 
@@ -173,8 +173,28 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
     ms_per_step = dev_ms / max(args.steps, 1)
-    # residual of the final state (device-side metric kernel if available, else skipped)
-    t = torch.tensor([ms_per_step, wall, float(infos[-1]["solver_resid"])], dtype=torch.float64, device="cuda")
+    # ---- e2e (EVERY rank): host buffers -> upload -> one sweep -> download, through the public linsolve() call.
+    # The e2e input is the state the timed steps started from (same per-sweep work as `value`), downloaded once
+    # outside the timed region and re-homed in pinned memory.
+    hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x_start.download())
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
+    e2e_kw = dict(nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov, x0_canonical=True, ctx=ctx,
+                  return_info=True, host_order="F")
+    xo = hx
+    if e2e_steps:
+        # one untimed pass of the same call: first-use costs of the host path (device blocks entering the caching
+        # allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
+        q.linsolve(hA, hb, hx, -lam, 1.0, **e2e_kw)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, **e2e_kw)
+        hx = xo   # chained like the device-resident steps: the e2e leg covers the same sweeps as `value`
+    barrier()
+    e2e_t = (time.perf_counter() - t0) / max(e2e_steps, 1)
+    h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)
+    d2h = sum(c.nbytes for c in xo)
+    t = torch.tensor([ms_per_step, wall, float(infos[-1]["solver_resid"]), e2e_t], dtype=torch.float64, device="cuda")
     if world > 1:
         gathered = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)     # NCCL over NVLink: residuals / timings only
@@ -182,6 +202,7 @@ def run_ours(args):
     else:
         allt = t.cpu().numpy()[None]
     ms_max = float(allt[:, 0].max())
+    e2e_t = float(allt[:, 3].max())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -214,26 +235,6 @@ def run_ours(args):
                 "peak_source": "measured FP64 DMMA.8x8x4 issue rate on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak_dmma_dfma.txt); "
                                "MEASURED_PEAKS.json carries no FP64 entry",
                 "matvec_tflops_inside_sweep_incl_krylov_svd_env": sweep_mv_tflops}
-    # ---- e2e: host buffers -> upload -> one sweep -> download
-    # the e2e input is the state the timed steps started from (same per-sweep work as `value`), downloaded once
-    # outside the timed region and re-homed in pinned memory
-    hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x_start.download())
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
-    xo = hx
-    if e2e_steps:
-        # one untimed pass of the same call: first-use costs of the host path (device blocks entering the caching
-        # allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
-        q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
-                   x0_canonical=True, ctx=ctx, return_info=True, host_order="F")
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
-                           x0_canonical=True, ctx=ctx, return_info=True, host_order="F")
-        hx = xo   # chained like the device-resident steps: the e2e leg covers the same sweeps as `value`
-    e2e_t = (time.perf_counter() - t0) / max(e2e_steps, 1)
-    h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)
-    d2h = sum(c.nbytes for c in xo)
     out = {
         "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -241,12 +242,16 @@ def run_ours(args):
         "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]): laplacian_mpo w=3, a0=-lambda (nk=%d), "
                                "maxdim=mindim=%d, cutoff=0, fixed-work GMRES %d Arnoldi steps/bond" % (n, chi, args.nk, chi, args.krylov),
                    "bonds_per_sweep": 2 * (n - 1), "matvecs_per_sweep": int(infos[-1]["matvecs"]),
-                   "instances": world, "l2": "256 MB buffer written between timed steps (L2 flush)",
+                   "instances": world, "instance_rule": "rank r solves wavenumber k_r = 2 pi (2^nk + r) from the same start vector",
+                   "ms_per_step_per_rank": [float(v) for v in allt[:, 0]],
+                   "l2": "256 MB buffer written between timed steps (L2 flush)",
                    "wall_s_timed_region": wall},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": ({"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "e2e": ({"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d) * world,
+                 "d2h_bytes_per_step": int(d2h) * world,
                  "note": "upload of A, b, x (pinned host cores) + one sweep + download of x, per step, through "
-                         "the public linsolve() call; the first x = the state the timed device-resident steps started from, then chained"}
+                         "the public linsolve() call on every rank (barrier on both sides, max over ranks; bytes summed over "
+                         "ranks); the first x = the state the timed device-resident steps started from, then chained"}
                 if e2e_steps else None),
         "roofline": roofline,
         "sweep": {"matvec_flops_per_sweep": flops_sweep, "maxlinkdim": int(infos[-1]["maxlinkdim"]),
