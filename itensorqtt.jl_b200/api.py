@@ -217,20 +217,28 @@ def add(x, y, *, alpha=1.0, beta=1.0, cutoff=1e-15, maxdim=None, mindim=1, ctx=N
     return cores
 
 
-def mps_to_vec(psi, ctx=None):
+def mps_to_vec(psi, ctx=None, out=None):
     """`mps_to_discrete_function(psi)` (reference src/function_to_mps.jl:136-145, one dimension) on the GPU -- the inverse of
     `vec_to_mps`: the 2^n grid values, site 1 = most significant bit, expanded by `qtt_mps_to_vec` and returned as a host array.
-    (`operators.mps_to_discrete_function` is the host-side restatement used for operand specs.)"""
+    (`operators.mps_to_discrete_function` is the host-side restatement used for operand specs.)
+    out: optional CUDA tensor / object with `data_ptr()` and `numel()` on the context's device that receives the values in
+    place (2^n float64, or 2^n complex128 for a complex chain); it is returned instead of a host array."""
     ctx = ctx or default_context()
     dp, fp = _as_dev_mps(psi, ctx)
     try:
         n = len(dp)
-        out = np.empty(1 << n, dtype=np.complex128 if dp.is_complex else np.float64)
-        check(ctx.handle, lib.qtt_mps_to_vec(ctx.handle, dp.handle, C.c_void_p(out.ctypes.data), 0))
+        if out is not None and hasattr(out, "data_ptr"):
+            need = (1 << n)
+            if int(out.numel()) != need:
+                raise ValueError(f"mps_to_vec: out has {int(out.numel())} elements, the chain has 2^{n} = {need} values")
+            check(ctx.handle, lib.qtt_mps_to_vec(ctx.handle, dp.handle, C.c_void_p(int(out.data_ptr())), 1))
+            return out
+        res = np.empty(1 << n, dtype=np.complex128 if dp.is_complex else np.float64)
+        check(ctx.handle, lib.qtt_mps_to_vec(ctx.handle, dp.handle, C.c_void_p(res.ctypes.data), 0))
+        return res
     finally:
         if fp:
             dp.free()
-    return out
 
 
 def sample(psi, idx, ctx=None):

@@ -547,7 +547,9 @@ int qtt_mps_to_vec(qtt_ctx* ctx, const qtt_mps* x, void* out, int32_t on_device)
     if (!on_device) QTT_CUDA(cudaMemcpyAsync(out, il, 2 * total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (total >= ((size_t)1 << 26)) pool_trim();
+  // multi-GB staging buffers (host output, planar complex planes) do not stay cached; a real chain written straight into
+  // the caller's device buffer staged nothing large
+  if (total >= ((size_t)1 << 26) && (!on_device || cplx)) pool_trim();
   QTT_CATCH(ctx)
 }
 
