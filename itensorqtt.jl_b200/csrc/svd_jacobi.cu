@@ -177,8 +177,16 @@ __device__ __forceinline__ double row_norm2(const JacobiArgs& a, int i, int lane
 }
 
 // NCH > 0: real rows held in registers; NCH == 0: real rows, two passes; NCH == -1: complex rows (planar), two passes
-template <int NCH>
-__global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
+// CL: the whole grid is ONE thread-block cluster (<= 8 CTAs of 8 warps) and the per-round barrier is the hardware cluster
+// barrier (release / acquire at cluster scope; the rows are accessed with .cg loads / stores, i.e. at L2) instead of the
+// software grid barrier: the rounds of a small 2k x 2k density matrix are barrier-bound (profiles/r01_launches_apply_dft.md).
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int NCH, bool CL>
+__global__ void __launch_bounds__(CL ? 256 : 64) jacobi_rows_kernel(JacobiArgs a) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -186,6 +194,10 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
   const int qe = (a.q + 1) & ~1;
   const int npairs = qe / 2, rounds = qe - 1;
   unsigned target = 0;
+  auto bar = [&]() {
+    if constexpr (CL) cluster_barrier();
+    else grid_sync(a.sync, target);
+  };
   int sweeps = 0;
   int converged = (a.q < 2) ? 1 : 0;
   // |Z|_F^2 (invariant under the rotations) sets the scale below which a row is numerically zero.  Without this a
@@ -195,12 +207,12 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
     double acc = row_norm2(a, i, lane);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
-  grid_sync(a.sync, target);
+  bar();
   double F2 = 0.0;
   for (int j = lane; j < a.q; j += 32) F2 += __ldcg(a.norms + j);
   F2 = warp_sum(F2);
   const double thr = a.zero_tol2 * F2;
-  grid_sync(a.sync, target);  // norms[] is rewritten after the sweeps
+  bar();  // norms[] is rewritten after the sweeps
   for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
     bool rotated = false;
     for (int r = 0; r < rounds; ++r) {
@@ -227,10 +239,10 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
         else rot = rotate_pair_cplx(ra, a.Zi + (size_t)ia * a.ld, rb, a.Zi + (size_t)ib * a.ld, a.ld, a.tol, thr, lane);
         rotated |= rot;
       }
-      grid_sync(a.sync, target);
+      bar();
     }
     if (rotated && lane == 0) atomicAdd(a.sync + 2 + sw, 1u);
-    grid_sync(a.sync, target);
+    bar();
     sweeps = sw + 1;
     if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
   }
@@ -241,9 +253,9 @@ __global__ void __launch_bounds__(64) jacobi_rows_kernel(JacobiArgs a) {
     if (a.eigen_mode) acc = sqrt(acc);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
-  grid_sync(a.sync, target);
+  bar();
   dev::rank_sort_desc(a.norms, a.q, a.q, a.sig2, a.perm);
-  grid_sync(a.sync, target);
+  bar();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double err;
     a.info[0] = dev::truncate_spectrum(a.sig2, a.q, a.cutoff, a.maxdim, a.mindim, &err);
@@ -279,9 +291,25 @@ __global__ void pad_rows_kernel(const double* __restrict__ src, int q, int p, in
 }
 
 template <int NCH>
-void launch_jacobi(Ctx* ctx, JacobiArgs& a, int grid) {
+void launch_jacobi(Ctx* ctx, JacobiArgs& a, int grid, int cluster_ctas) {
+  if (cluster_ctas > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_ctas);
+    cfg.blockDim = dim3(256);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QTT_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_kernel<NCH, true>, a));
+    ctx->launches++;
+    return;
+  }
   void* args[] = {&a};
-  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_rows_kernel<NCH>, dim3(grid), dim3(64), args, 0, ctx->stream));
+  QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_rows_kernel<NCH, false>, dim3(grid), dim3(64), args, 0, ctx->stream));
   ctx->launches++;
 }
 
@@ -331,12 +359,22 @@ RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, do
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
   if (grid < 1) grid = 1;
-  if (cplx) launch_jacobi<-1>(ctx, a, grid);
-  else if (ld <= 128) launch_jacobi<2>(ctx, a, grid);
-  else if (ld <= 256) launch_jacobi<4>(ctx, a, grid);
-  else if (ld <= 512) launch_jacobi<8>(ctx, a, grid);
-  else if (ld <= 1024) launch_jacobi<16>(ctx, a, grid);
-  else launch_jacobi<0>(ctx, a, grid);
+  // up to 64 row pairs (q <= 128): one cluster of <= 8 CTAs x 8 warps, one pair per warp and round, hardware cluster barrier per
+  // round (QTT_JACOBI_CLUSTER=0 restores the cooperative grid).  Measured on the DFT apply: n = 20, chi = 64 (2k <= 124)
+  // 26.4 -> 23.6 ms; with two pairs per warp (n = 24, chi = 128, 2k = 252) the 64 warps are work-bound and the grid of
+  // up to 148 two-warp CTAs wins (91 vs 117 ms), so larger problems keep the grid.
+  static const int cl_env = getenv("QTT_JACOBI_CLUSTER") ? atoi(getenv("QTT_JACOBI_CLUSTER")) : 1;
+  int cl = 0;
+  if (cl_env && npairs >= 2 && npairs <= 64) {
+    cl = (npairs + 7) / 8;
+    if (cl > 8) cl = 8;
+  }
+  if (cplx) launch_jacobi<-1>(ctx, a, grid, cl);
+  else if (ld <= 128) launch_jacobi<2>(ctx, a, grid, cl);
+  else if (ld <= 256) launch_jacobi<4>(ctx, a, grid, cl);
+  else if (ld <= 512) launch_jacobi<8>(ctx, a, grid, cl);
+  else if (ld <= 1024) launch_jacobi<16>(ctx, a, grid, cl);
+  else launch_jacobi<0>(ctx, a, grid, cl);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi launch failed: %s", cudaGetErrorString(e));
