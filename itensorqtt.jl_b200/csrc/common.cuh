@@ -254,7 +254,8 @@ struct RowSvd {
 RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, double cutoff, int maxdim, int mindim,
                    double* sigma_out, int max_sweeps, bool eigen_mode);
 bool svd_rows_qr_supported(int q, int p);
-RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps);
+RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps,
+                   bool eigen_mode = false);
 RowSvd svd_rows(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps);
 // phi [a][s1][s2][c] (device).  Writes A [a][s1][k] and B [k][s2][c] (device, capacity for k = min(2a, 2c)).
 SplitResult split2(Ctx* ctx, const double* phi, int chia, int chic, int ortho, double cutoff, int maxdim, int mindim,

@@ -317,6 +317,13 @@ void launch_jacobi(Ctx* ctx, JacobiArgs& a, int grid, int cluster_ctas) {
 
 RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, double cutoff, int maxdim, int mindim,
                    double* sigma_out, int max_sweeps, bool eigen_mode) {
+  // real Hermitian-PSD input (density matrices of a real `apply`: prolongation, retraction, real sums) of at least 32 rows:
+  // rank-revealing QR + block-cyclic Jacobi (svd_qr.cu) with the eigenvalue spectrum; QTT_EIGEN_QR=0 keeps the plain kernel
+  {
+    static const bool eig_qr = !(getenv("QTT_EIGEN_QR") && atoi(getenv("QTT_EIGEN_QR")) == 0);
+    if (eig_qr && eigen_mode && !Mi && q == p && q >= 32 && svd_rows_qr_supported(q, p))
+      return svd_rows_qr(ctx, M, q, p, cutoff, maxdim, mindim, sigma_out, max_sweeps, true);
+  }
   const int ld = (p + 1) & ~1;
   const int kmax = q < p ? q : p;
   const bool cplx = Mi != nullptr;

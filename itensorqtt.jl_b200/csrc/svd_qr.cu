@@ -399,6 +399,7 @@ struct JqArgs {
   int maxdim, mindim;
   const QrCtl* ctl;
   long long* dbg;  // optional (QTT_TRACE): cycle counters of CTA 0 [barrier, load, steps, store]
+  int eigen_mode;  // 1: the input is Hermitian PSD and the spectrum that is truncated is |row| (its eigenvalues), not |row|^2
 };
 
 // Jacobi rotation that orthogonalises two rows with |a|^2 = alpha, |b|^2 = beta, a.b = gamma: tan(theta) = t is the
@@ -534,6 +535,7 @@ __global__ void __launch_bounds__(64) jacobi_qr_kernel(JqArgs a) {
     }
     acc = warp_sum(acc);
     if (!(acc > thr)) acc = 0.0;
+    if (a.eigen_mode) acc = sqrt(acc);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
@@ -742,6 +744,7 @@ __global__ void __launch_bounds__(64 * JBT) jacobi_qr_block_kernel(JqArgs a) {
     }
     acc = warp_sum(acc);
     if (!(acc > thr)) acc = 0.0;
+    if (a.eigen_mode) acc = sqrt(acc);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
@@ -774,14 +777,14 @@ void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
 // operator exactly singular.
 __global__ void gather_rows_kernel(const double* __restrict__ Y, int ld, int off, int p, const int* __restrict__ perm,
                                    const double* __restrict__ sig2, int k, double* __restrict__ Wn, double* __restrict__ sigma_out,
-                                   const double* __restrict__ SE, int q, int ldp) {
+                                   const double* __restrict__ SE, int q, int ldp, int eigen_mode) {
   dev::pdl_wait();
   const int i = blockIdx.y;
   if (i >= k) return;
   const int src = perm[i];
   for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < p; col += gridDim.x * blockDim.x)
     Wn[(size_t)i * p + col] = src >= 0 ? Y[(size_t)src * ld + off + col] : SE[(size_t)(q + col) * ldp + i];
-  if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = sqrt(sig2[i]);
+  if (sigma_out && blockIdx.x == 0 && threadIdx.x == 0) sigma_out[i] = eigen_mode ? sig2[i] : sqrt(sig2[i]);
 }
 
 template <int NCH>
@@ -807,8 +810,10 @@ bool svd_rows_qr_supported(int q, int p) {
   return (p % 2 == 0) && q >= 1 && smem <= 200 * 1024;
 }
 
-RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps) {
+RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int maxdim, int mindim, double* sigma_out, int max_sweeps,
+                   bool eigen_mode) {
   QTT_REQUIRE(svd_rows_qr_supported(q, p), "svd_rows_qr: unsupported shape %d x %d", q, p);
+  QTT_REQUIRE(!eigen_mode || q == p, "svd_rows_qr: eigen mode needs a square matrix");
   const int ldp = (p + 1) & ~1;
   const int kmax = q < p ? q : p;
   const int qd = (q + 1) & ~1;
@@ -829,7 +834,10 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   double* derr = ctx->arena.alloc(2);
 
   const double tol = sqrt((double)p) * 1.1102230246251565e-16;
-  const double zt = 8.0 * tol;  // rows below zt * |Z|_F are rounding noise: never rotated, sigma reported as 0
+  // rows below zt * |Z|_F are rounding noise: never rotated, sigma reported as 0.  In eigen mode the truncated spectrum is
+  // |row| itself and the reference's cutoffs go down to 1e-15: the floor is kept as low as the rotation noise allows
+  // (same rule as svd_rows_ex).
+  const double zt = (eigen_mode ? 2.0 : 8.0) * tol;
   {
     int rows = q + p;
     int grid = (rows + 7) / 8;
@@ -882,6 +890,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   if (a.maxdim > kmax) a.maxdim = kmax;
   a.mindim = mindim;
   a.ctl = ctl;
+  a.eigen_mode = eigen_mode ? 1 : 0;
   a.dbg = nullptr;
   if (ctx->profiling && getenv("QTT_TRACE") != nullptr) {
     a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(8));
@@ -941,7 +950,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   res.Wn = ctx->arena.alloc((size_t)res.k * p);
   res.Wni = nullptr;
   dim3 grid2((p + 255) / 256, res.k);
-  launch_pdl(ctx, "gather_rows", gather_rows_kernel, grid2, dim3(256), 0, Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out, SE, q, ldp);
+  launch_pdl(ctx, "gather_rows", gather_rows_kernel, grid2, dim3(256), 0, Y, ldy, qd, p, perm, sig2, res.k, res.Wn, sigma_out, SE, q, ldp,
+             a.eigen_mode);
   return res;
 }
 
