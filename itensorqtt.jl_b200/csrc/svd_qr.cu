@@ -20,6 +20,7 @@
 #include "device_utils.cuh"
 #include <cstdlib>
 #include <string>
+#include <cooperative_groups.h>
 
 namespace qtt {
 namespace {
@@ -771,6 +772,589 @@ void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
   ctx->launches++;
 }
 
+// ---- blocked variant: Gram matrix of a block pair on the DMMA core, inner two-sided Jacobi in shared memory -----------
+// The row-cyclic kernels above pay one latency-bound step (barrier + L2 round trips, ~1.4-5.7 us) per 1-4 rotation rounds
+// whatever the row length: 128 grid barriers per sweep at r = 512.  Here the tournament is played between blocks of B = 32
+// rows.  One thread-block CLUSTER (8 CTAs) takes a block pair (64 rows); CTA c owns a column slab of the R part and of the
+// carried part.  Per round:
+//   1. partial Gram matrix (upper-triangular 8 x 8 tiles of the 64 x 64 matrix) of the R-part slab on the DMMA core; the
+//      accumulators are pushed straight into the staging buffer of the CTA that owns the entry (distributed shared memory),
+//      the owner adds the cs partial sums in rank order and pushes the result to every CTA, so all CTAs hold a bit-identical,
+//      exactly symmetric G;
+//   2. every CTA runs the same inner Jacobi on G in shared memory: the B^2 cross pairs (i in P, j in M) in B steps of B
+//      disjoint rotations, G <- Rot G Rot^T by symmetric 2 x 2 quads from one buffer into the other, while warp 0 already
+//      derives the rotations of the next step from the old buffer (one barrier per step).  Angles come from the updated
+//      Gram entries, which two-sided Jacobi keeps accurate relative to sqrt(g_ii g_jj) (Demmel-Veselic), and G is rebuilt
+//      from the rows themselves every round, so the accuracy of one-sided Jacobi is kept;
+//   3. the 32 x 32 recorded rotations are applied to the slab columns held in REGISTERS (one column = 64 doubles per thread,
+//      statically unrolled schedule, (c, s) broadcast from shared memory) and written straight back to global memory.
+// One grid barrier per round (15 per sweep at r = 512) moves the blocks between clusters through L2; the pairs inside a
+// block are swept once per sweep by a round with the in-block tournament (B - 1 steps, rotations accumulated into J and
+// applied as a DMMA GEMM).  Every row pair is still rotated exactly once per sweep (a cyclic one-sided Jacobi ordering).
+namespace cg = cooperative_groups;
+constexpr int GNT = 512;          // threads per CTA: warp 0 rotations, warps 1-7 Gram update, warps 8-15 slab columns in registers
+constexpr int GQT = 224;          // threads of the Gram-update warps
+constexpr int GAT = 256;          // threads of the slab warps: two adjacent lanes share one slab column
+constexpr int GAC = GAT / 2;      // slab columns they hold at a time
+constexpr int GNW = GNT / 32;
+
+// compile-time geometry for blocks of B rows
+template <int B>
+struct GG {
+  static constexpr int R = 2 * B;                 // rows of a block pair
+  static constexpr int H = B / 2;                 // rows per lane of a lane pair
+  static constexpr int JLD = R + 4;               // row stride of J (= 4 mod 16: conflict-free DMMA fragment loads)
+  static constexpr int LD = R + 1;                // row stride of G (odd: column accesses are conflict-free)
+  static constexpr int TRI = (B * (B + 1)) / 2;   // quads (row pair <= column pair) of the symmetric update
+  static constexpr int QPT = (TRI + GQT - 1) / GQT;  // quads per Gram-update thread
+  static constexpr int T8 = R / 8;                // 8 x 8 tiles per dimension
+  static constexpr int UT = (T8 * (T8 + 1)) / 2;  // upper-triangular tiles
+  static constexpr int TPW = (UT + GNW - 1) / GNW;   // tiles per warp
+  static constexpr int UTE = UT * 64;             // entries of the upper-triangular tiles
+};
+
+struct GjArgs {
+  JqArgs j;
+  int skip;        // measurement only (QTT_GRAM_SKIP): 1 = no Gram update, 2 = no slab rotations, 4 = slab rotations after the inner loop
+  int wR, wQ;      // slab widths (multiples of 8) of the R part and of the carried part per CTA
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+
+// Rotation from Gram entries (alpha, beta, gamma) without division or square root on the critical path of the inner loop:
+//   r = 1 / hypot(d, 2 gamma), cos(2 theta) = |d| r, c^2 = (1 + cos 2 theta) / 2, s = sign(d) gamma r / c,
+// with both reciprocal square roots taken from the hardware approximation (MUFU.RSQ64H, ~2^-22): the ANGLE only has to
+// be approximately right (the off-diagonal element shrinks by 1e-6 instead of vanishing; convergence stays quadratic
+// down to the 2.5e-15 threshold), what must hold to rounding is c^2 + s^2 = 1, and that is restored by two Newton
+// terms on e = c^2 + s^2 - 1 (|e| ~ 1e-6: e^3 is below double rounding).  Measured in isolation: 310 -> 150 cycles.
+__device__ __forceinline__ double rsqrt_approx(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ void grot(double alpha, double beta, double gamma, double& c, double& s) {
+  const double d = beta - alpha, g2 = 2.0 * gamma;
+  const double r = rsqrt_approx(d * d + g2 * g2);
+  const double c2 = 0.5 + 0.5 * (fabs(d) * r);
+  const double rc = rsqrt_approx(c2);
+  const double c0 = c2 * rc;
+  const double s0 = copysign(0.5 * r * rc, d) * g2;
+  const double e = fma(c0, c0, fma(s0, s0, -1.0));
+  const double k = fma(e, fma(e, 0.375, -0.5), 1.0);   // (1 + e)^(-1/2) = 1 - e/2 + 3 e^2 / 8 - ...
+  c = c0 * k;
+  s = s0 * k;
+}
+
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;\n" ::: "memory"); }
+
+// position of pair a of a step inside the (c, s) table: the two lanes of a lane pair (h = a / H) read adjacent entries
+template <int B>
+__device__ __forceinline__ int rpos(int a) { return ((a & (B / 2 - 1)) << 1) | (a / (B / 2)); }
+
+// The recorded rotations of a cross round applied to one slab column shared by two adjacent lanes (h = lane & 1).
+// Lane h keeps the P rows H h ... H h + H - 1 (xp) and a sliding window of H M rows (xm): in step t, P row a = H h + j meets
+// M row (a + t) mod B, which sits in slot (j + t) mod H of the SAME lane; after the step the two lanes swap slot t mod H
+// (M row t leaves lane 0 for lane 1, M row t + H comes back).  B doubles per lane instead of 2 B, all register indices static.
+// SYNC: one CTA barrier after every step (the column follows the inner Jacobi step by step, see the kernel).
+template <int B, bool SYNC>
+__device__ __forceinline__ void apply_cross(double (&xp)[B / 2], double (&xm)[B / 2], int h, const double2* __restrict__ cs2) {
+  constexpr int H = B / 2;
+  const double2* tab = cs2 + h;
+#pragma unroll
+  for (int t = 0; t < B; ++t) {
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const double2 r = tab[t * B + 2 * j];
+      const double u = xp[j], v = xm[(j + t) & (H - 1)];
+      xp[j] = r.x * u - r.y * v;
+      xm[(j + t) & (H - 1)] = r.y * u + r.x * v;
+    }
+    xm[t & (H - 1)] = __shfl_xor_sync(0xffffffffu, xm[t & (H - 1)], 1);
+    if (SYNC) cta_bar();
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
+  using K = GG<B>;
+  constexpr int GR = K::R, GLD = K::LD, GJLD = K::JLD, H = K::H;
+  const JqArgs& a = ga.j;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wR = ga.wR, wQ = ga.wQ, W = wR + wQ, SLD = wR + 4;
+  extern __shared__ __align__(16) double gsm[];
+  double* S = gsm;                      // [GR][SLD] R-part slab (Gram operand)
+  double* A = S + (size_t)GR * SLD;     // region A [GR * GJLD]: staging of the reduce; then (c, s) tables (cross) or J (inside-block round)
+  double* G0 = A + GR * GJLD;           // [GR][GLD]
+  double* G1 = G0 + GR * GLD;           // [GR][GLD]  (cross rounds: only the entries (i, j), i <= j, of G0 / G1 are maintained)
+  double2* cs2 = reinterpret_cast<double2*>(A);  // [B steps][B pairs at rpos()]
+  double* J = A;
+  __shared__ unsigned char tri_r[K::TRI], tri_c[K::TRI];
+  __shared__ int plo[2][B], phi[2][B];
+  __shared__ double pc[2][B], ps[2][B];
+  __shared__ int s_any;
+  for (int k = tid; k < K::TRI; k += GNT) {
+    int r = 0, rem = k;
+    while (rem >= B - r) { rem -= B - r; ++r; }
+    tri_r[k] = (unsigned char)r;
+    tri_c[k] = (unsigned char)(r + rem);
+  }
+  __syncthreads();
+  // static work assignment: Gram-update thread qt owns the quads qt, qt + 224, ... of the triangular enumeration
+  const bool is_quad = warp >= 1 && warp < 1 + GQT / 32;
+  const bool is_apply = warp >= GNW - GAT / 32;
+  const int qt = tid - 32, at = tid - (GNT - GAT), acol = at >> 1, ah = at & 1;
+  int qra[K::QPT], qcb[K::QPT];
+  bool qok[K::QPT];
+#pragma unroll
+  for (int u = 0; u < K::QPT; ++u) {
+    const int k = qt + u * GQT;
+    qok[u] = is_quad && k < K::TRI;
+    qra[u] = qok[u] ? tri_r[k] : 0;
+    qcb[u] = qok[u] ? tri_c[k] : 0;
+  }
+  // Gram tiles of this warp: tl = warp, warp + 16, ... of the upper-triangular 8 x 8 tiles
+  int gti[K::TPW], gtj[K::TPW];
+#pragma unroll
+  for (int u = 0; u < K::TPW; ++u) {
+    int ti = 0, rem = warp + u * GNW;
+    if (rem >= K::UT) rem = K::UT - 1;   // masked below
+    while (rem >= K::T8 - ti) { rem -= K::T8 - ti; ++ti; }
+    gti[u] = ti; gtj[u] = ti + rem;
+  }
+
+  const int q = a.ctl->r;
+  const double thr = a.ctl->thr;
+  const double tol2 = a.tol * a.tol;
+  const int nbk = (((q + B - 1) / B) + 1) & ~1;
+  const int nslots = nbk / 2, orounds = nbk - 1;
+  const int ld = a.ld, ndot = a.ndot;
+  const int cR0 = crank * wR, cQ0 = ndot + crank * wQ;   // this CTA's global column ranges
+  const int per = K::UTE / cs;                             // entries of the upper-triangular tiles owned per CTA (cs divides UTE, per even)
+  unsigned target = 0;
+  int sweeps = 0;
+  int converged = (q < 2) ? 1 : 0;
+  __syncthreads();
+  for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
+    bool rotated = false;
+    for (int R = -1; R < orounds; ++R) {   // R = -1: pairs inside the blocks
+      for (int slot = cid; slot < nslots; slot += ncl) {
+        int bp, bm;
+        if (R < 0) { bp = 2 * slot; bm = 2 * slot + 1; }
+        else if (slot == 0) { bp = R; bm = nbk - 1; }
+        else { bp = (R + slot) % (nbk - 1); bm = (R - slot + (nbk - 1)) % (nbk - 1); }
+        auto grow = [&](int i) { return i < B ? bp * B + i : bm * B + (i - B); };
+        const bool dbg = a.dbg && blockIdx.x == 0 && tid == 0;
+        long long tc = dbg ? clock64() : 0;
+        auto lap = [&](int slot_) { if (dbg) { long long n = clock64(); a.dbg[slot_] += n - tc; tc = n; } };
+        // slab column of the register warps (cross rounds): requested now, used after the Gram / reduce phases
+        double xp[H], xm[H];
+        auto col_of = [&](int c, int& gc) { gc = c < wR ? cR0 + c : cQ0 + (c - wR); return c < W && gc < (c < wR ? ndot : ld); };
+        auto col_load = [&](int gc, bool ok) {
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
+            xp[j] = (ok && gp < q) ? __ldcg(a.Y + (size_t)gp * ld + gc) : 0.0;
+            xm[j] = (ok && gm < q) ? __ldcg(a.Y + (size_t)gm * ld + gc) : 0.0;
+          }
+        };
+        auto col_store = [&](int gc, bool ok) {
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
+            if (ok && gp < q) __stcg(a.Y + (size_t)gp * ld + gc, xp[j]);
+            if (ok && gm < q) __stcg(a.Y + (size_t)gm * ld + gc, xm[j]);
+          }
+        };
+        bool xok = false;
+        int xgc = 0;
+        if (R >= 0 && is_apply) {
+          xok = col_of(acol, xgc);
+          col_load(xgc, xok);
+        }
+        // ---- 1. R-part slab load (cp.async, zero fill beyond the rank / the row length)
+        {
+          const int cpr = wR / 2;  // 16-byte chunks per slab row
+          for (int id = tid; id < GR * cpr; id += GNT) {
+            const int i = id / cpr, c = (id % cpr) * 2;
+            const int gi = grow(i), gc = cR0 + c;
+            const bool ok = gi < q && gc < ndot;
+            cp_async16(S + (size_t)i * SLD + c, ok ? a.Y + (size_t)gi * ld + gc : a.Y, ok ? 16 : 0);
+          }
+          asm volatile("cp.async.commit_group;\n" ::);
+          asm volatile("cp.async.wait_group 0;\n" ::);
+          __syncthreads();
+        }
+        lap(1);
+        // ---- 2. partial Gram, upper-triangular tiles only, pushed to the owners' staging buffers
+        {
+          double acc[K::TPW][2] = {};
+          const double* sa[K::TPW];
+          const double* sb[K::TPW];
+#pragma unroll
+          for (int u = 0; u < K::TPW; ++u) {
+            sa[u] = S + (size_t)(gti[u] * 8 + g) * SLD + t4;
+            sb[u] = S + (size_t)(gtj[u] * 8 + g) * SLD + t4;
+          }
+          if (warp < K::UT) {
+            for (int k0 = 0; k0 < wR; k0 += 4) {
+#pragma unroll
+              for (int u = 0; u < K::TPW; ++u) dmma884(acc[u][0], acc[u][1], sa[u][k0], sb[u][k0]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < K::TPW; ++u) {
+            if (warp + u * GNW >= K::UT) continue;
+            const int idx = (warp + u * GNW) * 64 + g * 8 + 2 * t4;   // (tile, row g, columns 2 t4, 2 t4 + 1)
+            double* dst = cluster.map_shared_rank(A, idx / per) + crank * per + (idx % per);   // per is even: the pair stays together
+            *reinterpret_cast<double2*>(dst) = make_double2(acc[u][0], acc[u][1]);
+          }
+        }
+        lap(2);
+        cluster.sync();
+        lap(3);
+        // ---- 3. owner: sum the cs partials in rank order, push the entry and its mirror to every CTA of the cluster
+        for (int e = tid; e < per; e += GNT) {
+          double sum = 0.0;
+          for (int k = 0; k < cs; ++k) sum += A[k * per + e];
+          const int idx = crank * per + e;
+          const int tl = idx >> 6, within = idx & 63;
+          int ti = 0, rem = tl;
+          while (rem >= K::T8 - ti) { rem -= K::T8 - ti; ++ti; }
+          const int tj = ti + rem;
+          const int i = ti * 8 + (within >> 3), jx = tj * 8 + (within & 7);
+          for (int k = 0; k < cs; ++k) {
+            double* Gk = cluster.map_shared_rank(G0, k);
+            Gk[i * GLD + jx] = sum;
+            Gk[jx * GLD + i] = sum;
+          }
+        }
+        cluster.sync();
+        lap(4);
+        // ---- 4. anything to rotate?  (identical decision in every CTA of the cluster: G is bit-identical)
+        const bool intra = R < 0;
+        {
+          int cand = 0;
+          for (int e = tid; e < GR * GR; e += GNT) {
+            const int i = e / GR, jx = e % GR;
+            const bool pairok = intra ? (i < jx && (i / B) == (jx / B)) : (i < B && jx >= B);
+            if (pairok) {
+              const double gii = G0[i * GLD + i], gjj = G0[jx * GLD + jx], gij = G0[i * GLD + jx];
+              cand |= (gii > thr) && (gjj > thr) && (gij * gij > tol2 * (gii * gjj));
+            }
+          }
+          if (tid == 0) s_any = 0;
+          if (!__syncthreads_or(cand)) continue;
+        }
+        lap(5);
+        if (!intra) {
+          // ---- 5a. cross round: B steps; step t pairs row a (P) with row B + (a + t) mod B (M).  Per step ONE barrier:
+          //   warp 0       rotations of step t + 1 from the buffer that step t reads (look-ahead through the bilinear form)
+          //   warps 1-7    G <- Rot G Rot^T, symmetric quads (statically assigned), upper triangle, buffer to buffer
+          //   warps 8-15   the rotations of step t on the slab columns, in registers
+          // Every role runs its own branch-free loop (a taken branch costs the lone look-ahead warp an instruction fetch:
+          // measured ~50 cycles each, ten of them per step in the first version of this loop).
+          int anyrot = 0;
+          if (warp == 0) {
+            const int lo = lane & (B - 1), hi = B + lo;
+            const double al = G0[lo * GLD + lo], be = G0[hi * GLD + hi], gm = G0[lo * GLD + hi];
+            double c, s;
+            const bool rot = lane < B && (al > thr) && (be > thr) && (gm * gm > tol2 * (al * be));
+            grot(al, be, gm, c, s);
+            if (lane < B) cs2[rpos<B>(lane)] = rot ? make_double2(c, s) : make_double2(1.0, 0.0);
+            anyrot |= rot;
+          }
+          __syncthreads();
+          if (is_apply) {
+            if (ga.skip & 6) {
+              for (int st = 0; st < B; ++st) cta_bar();
+              if (ga.skip & 4) apply_cross<B, false>(xp, xm, ah, cs2);   // A/B: rotations applied after the loop
+            } else {
+              apply_cross<B, true>(xp, xm, ah, cs2);
+            }
+          } else if (warp == 0) {
+            // look-ahead: entries (lo, lo), (hi, hi), (lo, hi) of the NEXT matrix from the buffer step st reads,
+            // G'[x][y] = sum_{x' in {x, px}} sum_{y' in {y, py}} k_x(x') k_y(y') G[x'][y']   (stored entries: row index <= column index).
+            // The last pass (st = B - 1) writes a table row nobody reads.
+            const int x_ = lane & (B - 1);
+            long long tcomp = 0, tbar = 0, tprev = a.dbg ? clock64() : 0;
+#pragma unroll 1
+            for (int st = 0; st < B; ++st) {
+              const double* __restrict__ Gc = (st & 1) ? G1 : G0;
+              const double2* rt = cs2 + st * B;
+              const int y_ = B + ((x_ + st + 1) & (B - 1));
+              const int px = B + ((x_ + st) & (B - 1));          // partner of P row x in step st
+              const int ay = (y_ - B - st) & (B - 1);             // pair index of M row y in step st; its partner is row ay
+              const double2 rx = rt[rpos<B>(x_)], ry = rt[rpos<B>(ay)];
+              const double kx0 = rx.x, kx1 = -rx.y;              // G'[x] = c G[x] - s G[px]
+              const double ky0 = ry.x, ky1 = ry.y;               // G'[y] = c G[y] + s G[ay]
+              const int xa0 = min(x_, ay), xa1 = max(x_, ay);
+              const int py0 = min(px, y_), py1 = max(px, y_);
+              const double gxx = Gc[x_ * GLD + x_], gxp = Gc[x_ * GLD + px], gpp = Gc[px * GLD + px];
+              const double gyy = Gc[y_ * GLD + y_], gya = Gc[ay * GLD + y_], gaa = Gc[ay * GLD + ay];
+              const double gxy = Gc[x_ * GLD + y_], gxa = Gc[xa0 * GLD + xa1], gpy = Gc[py0 * GLD + py1], gpa = Gc[ay * GLD + px];
+              const double al = kx0 * (kx0 * gxx + kx1 * gxp) + kx1 * (kx0 * gxp + kx1 * gpp);
+              const double be = ky0 * (ky0 * gyy + ky1 * gya) + ky1 * (ky0 * gya + ky1 * gaa);
+              const double gm = kx0 * (ky0 * gxy + ky1 * gxa) + kx1 * (ky0 * gpy + ky1 * gpa);
+              double c, s;
+              const bool rot = lane < B && st + 1 < B && (al > thr) && (be > thr) && (gm * gm > tol2 * (al * be));
+              grot(al, be, gm, c, s);
+              if (lane < B) cs2[(st + 1) * B + rpos<B>(lane)] = rot ? make_double2(c, s) : make_double2(1.0, 0.0);
+              anyrot |= rot;
+              if (a.dbg) { const long long t1 = clock64(); tcomp += t1 - tprev; tprev = t1; }
+              cta_bar();
+              if (a.dbg) { const long long t1 = clock64(); tbar += t1 - tprev; tprev = t1; }
+            }
+            if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[9] += tcomp; a.dbg[10] += tbar; }
+          } else if (is_quad && !(ga.skip & 1)) {
+#pragma unroll 1
+            for (int st = 0; st < B; ++st) {
+              const double* __restrict__ Gc = (st & 1) ? G1 : G0;
+              double* __restrict__ Gn = (st & 1) ? G0 : G1;
+              const double2* rt = cs2 + st * B;
+              double gq[K::QPT][4];
+              double2 r1[K::QPT], r2[K::QPT];
+              int o00[K::QPT], o01[K::QPT], o10[K::QPT], o11[K::QPT];
+#pragma unroll
+              for (int u = 0; u < K::QPT; ++u) {
+                // rows {ia, ja} x columns {ib, jb}, ia <= ib < B <= ja, jb; stored positions have row index <= column index.
+                // Threads without a quad (qok false) recompute quad 0 and do not store.
+                const int ia = qra[u], ja = B + ((qra[u] + st) & (B - 1)), ib = qcb[u], jb = B + ((qcb[u] + st) & (B - 1));
+                o00[u] = ia * GLD + ib; o01[u] = ia * GLD + jb; o10[u] = ib * GLD + ja;
+                o11[u] = min(ja, jb) * GLD + max(ja, jb);
+                r1[u] = rt[rpos<B>(qra[u])]; r2[u] = rt[rpos<B>(qcb[u])];
+                gq[u][0] = Gc[o00[u]]; gq[u][1] = Gc[o01[u]]; gq[u][2] = Gc[o10[u]]; gq[u][3] = Gc[o11[u]];
+              }
+#pragma unroll
+              for (int u = 0; u < K::QPT; ++u) {
+                const double t00 = r1[u].x * gq[u][0] - r1[u].y * gq[u][2], t01 = r1[u].x * gq[u][1] - r1[u].y * gq[u][3];
+                const double t10 = r1[u].y * gq[u][0] + r1[u].x * gq[u][2], t11 = r1[u].y * gq[u][1] + r1[u].x * gq[u][3];
+                if (qok[u]) {
+                  Gn[o00[u]] = r2[u].x * t00 - r2[u].y * t01;
+                  Gn[o01[u]] = r2[u].y * t00 + r2[u].x * t01;
+                  if (qra[u] != qcb[u]) Gn[o10[u]] = r2[u].x * t10 - r2[u].y * t11;   // diagonal quad: (ib, ja) is (ia, jb)
+                  Gn[o11[u]] = r2[u].y * t10 + r2[u].x * t11;
+                }
+              }
+              cta_bar();
+            }
+          } else {
+#pragma unroll 1
+            for (int st = 0; st < B; ++st) cta_bar();
+          }
+          if (warp == 0 && __any_sync(0xffffffffu, anyrot) && lane == 0) s_any = 1;
+          __syncthreads();
+          lap(6);
+          if (s_any) {
+            rotated = true;
+            // ---- 6a. the register columns go straight back to global memory; slab columns beyond the 128 register columns
+            //          (chi = 512) are rotated afterwards from the complete table
+            if (is_apply) {
+              col_store(xgc, xok);
+              for (int c0 = GAC; c0 < W; c0 += GAC) {   // warp-uniform trip count: the lane pairs exchange rows by shuffle
+                int gc;
+                const bool ok = col_of(c0 + acol, gc);
+                col_load(gc, ok);
+                apply_cross<B, false>(xp, xm, ah, cs2);
+                col_store(gc, ok);
+              }
+            }
+          }
+          lap(7);
+        } else {
+          // ---- 5b. pairs inside the two blocks: B - 1 round-robin steps on G0 in place, rotations accumulated into J
+          for (int e = tid; e < GR * GJLD; e += GNT) J[e] = ((e / GJLD) == (e % GJLD)) ? 1.0 : 0.0;
+          auto make_rot = [&](int st, int par) {   // warp 0, lanes < B: B / 2 pairs per block
+            const int l = lane & (B - 1);
+            const int blk = l / H, i = l % H;
+            int u0, u1;
+            if (i == 0) { u0 = st; u1 = B - 1; }
+            else { u0 = (st + i) % (B - 1); u1 = (st - i + (B - 1)) % (B - 1); }
+            const int lo = blk * B + (u0 < u1 ? u0 : u1), hi = blk * B + (u0 < u1 ? u1 : u0);
+            const double al = G0[lo * GLD + lo], be = G0[hi * GLD + hi], gm = G0[lo * GLD + hi];
+            double c = 1.0, s = 0.0;
+            const bool rot = lane < B && (al > thr) && (be > thr) && (gm * gm > tol2 * (al * be));
+            if (rot) grot(al, be, gm, c, s);
+            if (lane < B) { plo[par][lane] = lo; phi[par][lane] = hi; pc[par][lane] = c; ps[par][lane] = s; }
+            if (__any_sync(0xffffffffu, rot) && lane == 0) s_any = 1;
+          };
+          __syncthreads();
+          if (warp == 0) make_rot(0, 0);
+          __syncthreads();
+          for (int st = 0; st < B - 1; ++st) {
+            const int par = st & 1;
+            for (int qd = tid; qd < B * B; qd += GNT) {
+              const int ra = qd / B, cb = qd % B;
+              const int ia = plo[par][ra], ja = phi[par][ra], ib = plo[par][cb], jb = phi[par][cb];
+              const double ca = pc[par][ra], sa = ps[par][ra], cc = pc[par][cb], sc = ps[par][cb];
+              const double g00 = G0[ia * GLD + ib], g01 = G0[ia * GLD + jb], g10 = G0[ja * GLD + ib], g11 = G0[ja * GLD + jb];
+              const double t00 = ca * g00 - sa * g10, t01 = ca * g01 - sa * g11;
+              const double t10 = sa * g00 + ca * g10, t11 = sa * g01 + ca * g11;
+              G0[ia * GLD + ib] = cc * t00 - sc * t01;
+              G0[ia * GLD + jb] = sc * t00 + cc * t01;
+              G0[ja * GLD + ib] = cc * t10 - sc * t11;
+              G0[ja * GLD + jb] = sc * t10 + cc * t11;
+            }
+            __syncthreads();
+            if (warp == 0) {
+              if (st + 1 < B - 1) make_rot(st + 1, par ^ 1);
+            } else {
+              for (int e = tid - 32; e < GR * B; e += GNT - 32) {
+                const int m = e / B, cb = e % B;
+                const int ib = plo[par][cb], jb = phi[par][cb];
+                const double cc = pc[par][cb], sc = ps[par][cb];
+                const double x = J[m * GJLD + ib], y = J[m * GJLD + jb];
+                J[m * GJLD + ib] = cc * x - sc * y;
+                J[m * GJLD + jb] = sc * x + cc * y;
+              }
+            }
+            __syncthreads();
+          }
+          lap(6);
+          if (s_any) {
+            rotated = true;
+            // ---- 6b. slab <- J^T slab (DMMA), B operand read from global memory, one 8-column strip per warp pass
+            for (int strip = warp; strip < W / 8; strip += GNW) {
+              const int n0 = strip * 8;
+              const int cb = n0 < wR ? cR0 + n0 : cQ0 + (n0 - wR);
+              const int lim = n0 < wR ? ndot : ld;
+              double acc[K::T8][2] = {};
+              for (int k0 = 0; k0 < GR; k0 += 4) {
+                const int gk = grow(k0 + t4);
+                const double bv = (gk < q && cb + g < lim) ? __ldcg(a.Y + (size_t)gk * ld + cb + g) : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < K::T8; ++mt) {
+                  const double av = J[(k0 + t4) * GJLD + mt * 8 + g];
+                  dmma884(acc[mt][0], acc[mt][1], av, bv);
+                }
+              }
+              __syncwarp();
+              const int gc = cb + 2 * t4;
+              if (gc < lim) {
+#pragma unroll
+                for (int mt = 0; mt < K::T8; ++mt) {
+                  const int gi = grow(mt * 8 + g);
+                  if (gi < q) __stcg(reinterpret_cast<double2*>(a.Y + (size_t)gi * ld + gc), make_double2(acc[mt][0], acc[mt][1]));
+                }
+              }
+            }
+          }
+          lap(7);
+        }
+        if (nslots > ncl) cluster.sync();   // region A / G0 are reused by this cluster's next slot
+      }
+      {
+        long long tb0 = clock64();
+        grid_sync(a.sync, target);
+        if (a.dbg && blockIdx.x == 0 && tid == 0) { a.dbg[0] += clock64() - tb0; a.dbg[8] += 1; }
+      }
+    }
+    if (rotated && tid == 0 && crank == 0) atomicAdd(a.sync + 2 + sw, 1u);
+    grid_sync(a.sync, target);
+    sweeps = sw + 1;
+    if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
+  }
+  const int gw = blockIdx.x * GNW + warp;
+  const int GW = gridDim.x * GNW;
+  for (int i = gw; i < q; i += GW) {
+    const double* ri = a.Y + (size_t)i * a.ld;
+    double acc = 0.0;
+    for (int col = 2 * lane; col < a.ndot; col += 64) {
+      double2 v = __ldcg(reinterpret_cast<const double2*>(ri + col));
+      acc += v.x * v.x + v.y * v.y;
+    }
+    acc = warp_sum(acc);
+    if (!(acc > thr)) acc = 0.0;
+    if (a.eigen_mode) acc = sqrt(acc);
+    if (lane == 0) __stcg(a.norms + i, acc);
+  }
+  grid_sync(a.sync, target);
+  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
+  grid_sync(a.sync, target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double err;
+    a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
+    a.info[1] = sweeps;
+    a.info[2] = converged;
+    a.info[3] = q;
+    a.derr[0] = err;
+  }
+}
+
+// Launch: one cluster of 8 CTAs per block pair (cluster size 16 fits only 7 times on a B200: measured).
+template <int B>
+bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int kmax) {
+  using K = GG<B>;
+  const int nbk = (((kmax + B - 1) / B) + 1) & ~1;
+  const int nslots = nbk / 2;
+  const int lq = a.ld - a.ndot;
+  const int cs = 8;
+  const int wR = (((a.ndot + cs - 1) / cs) + 7) & ~7;
+  const int wQ = (((lq + cs - 1) / cs) + 7) & ~7;
+  const size_t smem = ((size_t)K::R * (wR + 4) + (size_t)K::R * K::JLD + (size_t)2 * K::R * K::LD) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  static DevOnce once;
+  static int maxcl[64] = {};
+  const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+  if (once.first(ctx->device)) {
+    QTT_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * 8);
+    cfg.blockDim = dim3(GNT);
+    cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, jacobi_gram_kernel<B>, &cfg) != cudaSuccess) n = 0;
+    (void)cudaGetLastError();
+    maxcl[dv] = n;
+  }
+  if (maxcl[dv] < 1) return false;
+  const int ncl = nslots < maxcl[dv] ? nslots : maxcl[dv];
+  GjArgs ga;
+  ga.j = a; ga.wR = wR; ga.wQ = wQ;
+  ga.skip = getenv("QTT_GRAM_SKIP") ? atoi(getenv("QTT_GRAM_SKIP")) : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ncl * cs);
+  cfg.blockDim = dim3(GNT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, jacobi_gram_kernel<B>, ga);
+  if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi_gram launch failed (%d clusters x %d): %s", ncl, cs, cudaGetErrorString(e));
+  if (a.dbg) fprintf(stderr, "[qtt trace]   gram jacobi B=%d: %d clusters x %d CTAs (max active %d), slab %d + %d columns, %zu B smem\n", B, ncl, cs, maxcl[dv], wR, wQ, smem);
+  ctx->launches++;
+  return true;
+}
+
+// r = the numerical rank the QR found (read back by the caller): blocks of 16 rows while every block pair gets its own
+// cluster (measured on B200: 15 co-resident clusters of 8, i.e. r <= 480), blocks of 32 beyond.  Measured, 512 x 512 splits:
+// graded spectrum (r = 256) 3.9 ms with blocks of 32 / 2.7 ms with blocks of 16; flat spectrum (r = 512) 9.0 / 10.8 ms.
+bool launch_jq_gram(Ctx* ctx, JqArgs& a, int r) {
+  static const int bsel = getenv("QTT_JACOBI_B") ? atoi(getenv("QTT_JACOBI_B")) : 0;
+  const int slots16 = ((((r + 15) / 16) + 1) & ~1) / 2;
+  if (bsel == 16 || (bsel == 0 && slots16 <= 15)) {
+    if (launch_jq_gram_b<16>(ctx, a, r)) return true;
+  }
+  return launch_jq_gram_b<32>(ctx, a, r);
+}
+
 // Wn[i][:] = carried (Q^T) part of row perm[i].  Positions beyond the numerical rank r (sigma = 0, kept only because of
 // `mindim`) receive the orthonormal completion LAPACK's SVD would return there: column i of the accumulated Q (the identity
 // block of SE), which is orthogonal to the first r columns.  A zero row instead would make the next bond's projected
@@ -893,15 +1477,25 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   a.eigen_mode = eigen_mode ? 1 : 0;
   a.dbg = nullptr;
   if (ctx->profiling && getenv("QTT_TRACE") != nullptr) {
-    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(8));
-    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 64, ctx->stream));
+    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(16));
+    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 128, ctx->stream));
   }
   const int npairs = ((kmax + 1) & ~1) / 2;
   int grid = (npairs + 1) / 2;
   if (grid > ctx->sms) grid = ctx->sms;
   if (grid < 1) grid = 1;
   const int half = qd > ldp ? qd : ldp;  // the longer of the two row parts
-  if (half <= 1024 && kmax >= 16) {
+  static const bool gram_off = getenv("QTT_JACOBI") != nullptr && std::string(getenv("QTT_JACOBI")) == "cyclic";
+  bool launched = false;
+  if (!gram_off && kmax >= 64 && kmax <= 2048) {
+    // the grid and the block size follow the numerical rank: one 4-byte read-back (the split synchronises for the kept rank anyway)
+    int* h_r = reinterpret_cast<int*>(ctx->h_scal + 16);
+    QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*h_r >= 32) launched = launch_jq_gram(ctx, a, *h_r);
+  }
+  if (launched) {
+  } else if (half <= 1024 && kmax >= 16) {
     // block-cyclic kernel: one CTA (4 warp pairs) per pair of 4-row blocks
     const int nb4 = (((kmax + JB - 1) / JB) + 1) & ~1;
     int g4 = nb4 / 2;
@@ -933,9 +1527,14 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     cudaEventElapsedTime(&ms, evq, evj);
     fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: numerical rank %d, jacobi %d sweeps %.3f ms (after QR)\n", q, p, h_info[3], h_info[1], ms);
     if (a.dbg) {
-      long long h[8];
-      cudaMemcpy(h, a.dbg, 64, cudaMemcpyDeviceToHost);
-      if (h[4] > 0)
+      long long h[16];
+      cudaMemcpy(h, a.dbg, 128, cudaMemcpyDeviceToHost);
+      if (h[8] > 0)
+        fprintf(stderr, "[qtt trace]   gram jacobi CTA0 cycles per round: barrier %.0f load %.0f gram %.0f csync1 %.0f reduce %.0f check %.0f inner %.0f apply %.0f (%lld rounds)\n",
+                (double)h[0] / h[8], (double)h[1] / h[8], (double)h[2] / h[8], (double)h[3] / h[8], (double)h[4] / h[8], (double)h[5] / h[8],
+                (double)h[6] / h[8], (double)h[7] / h[8], h[8]);
+      if (h[8] > 0) fprintf(stderr, "[qtt trace]   per round: look-ahead warp computing %.0f, waiting at the step barrier %.0f cycles\n", (double)h[9] / h[8], (double)h[10] / h[8]);
+      else if (h[4] > 0)
         fprintf(stderr, "[qtt trace]   block jacobi CTA0 cycles per outer round: barrier %.0f load %.0f steps %.0f store %.0f (%lld rounds)\n",
                 (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
     }
