@@ -792,10 +792,13 @@ void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
 // block are swept once per sweep by a round with the in-block tournament (B - 1 steps, rotations accumulated into J and
 // applied as a DMMA GEMM).  Every row pair is still rotated exactly once per sweep (a cyclic one-sided Jacobi ordering).
 namespace cg = cooperative_groups;
-constexpr int GNT = 512;          // threads per CTA: warp 0 rotations, warps 1-7 Gram update, warps 8-15 slab columns in registers
-constexpr int GQT = 224;          // threads of the Gram-update warps
-constexpr int GAT = 256;          // threads of the slab warps: two adjacent lanes share one slab column
-constexpr int GAC = GAT / 2;      // slab columns they hold at a time
+// Threads per CTA and their roles in the inner loop.  The look-ahead warp (warp 0) is latency-critical: a dependent chain of
+// ~45 FP64 operations per step.  The warps that share its scheduler / FP64 pipe (warps 4, 8, 12) therefore stay idle in the
+// loop (measured: the look-ahead step 1200 -> 600 cycles at B = 32): Gram update on warps 1-3 and 5-7, slab columns in
+// registers on warps 9-11 and 13-15.
+constexpr int GNT = 512;
+constexpr int GQT = 192;          // threads of the Gram-update warps
+constexpr int GAT = 192;          // threads of the slab warps: two adjacent lanes share one slab column
 constexpr int GNW = GNT / 32;
 
 // compile-time geometry for blocks of B rows
@@ -811,6 +814,7 @@ struct GG {
   static constexpr int UT = (T8 * (T8 + 1)) / 2;  // upper-triangular tiles
   static constexpr int TPW = (UT + GNW - 1) / GNW;   // tiles per warp
   static constexpr int UTE = UT * 64;             // entries of the upper-triangular tiles
+  static constexpr int NC = B <= 16 ? 2 : 1;      // slab columns per lane pair of the register warps
 };
 
 struct GjArgs {
@@ -853,6 +857,7 @@ __device__ __forceinline__ void grot(double alpha, double beta, double gamma, do
 
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;\n" ::: "memory"); }
 
+
 // position of pair a of a step inside the (c, s) table: the two lanes of a lane pair (h = a / H) read adjacent entries
 template <int B>
 __device__ __forceinline__ int rpos(int a) { return ((a & (B / 2 - 1)) << 1) | (a / (B / 2)); }
@@ -862,8 +867,9 @@ __device__ __forceinline__ int rpos(int a) { return ((a & (B / 2 - 1)) << 1) | (
 // M row (a + t) mod B, which sits in slot (j + t) mod H of the SAME lane; after the step the two lanes swap slot t mod H
 // (M row t leaves lane 0 for lane 1, M row t + H comes back).  B doubles per lane instead of 2 B, all register indices static.
 // SYNC: one CTA barrier after every step (the column follows the inner Jacobi step by step, see the kernel).
-template <int B, bool SYNC>
-__device__ __forceinline__ void apply_cross(double (&xp)[B / 2], double (&xm)[B / 2], int h, const double2* __restrict__ cs2) {
+// NC slab columns per lane pair share every (c, s) load (blocks of 16 rows: 2 columns = 32 doubles per lane).
+template <int B, int NC, bool SYNC>
+__device__ __forceinline__ void apply_cross(double (&xp)[NC][B / 2], double (&xm)[NC][B / 2], int h, const double2* __restrict__ cs2) {
   constexpr int H = B / 2;
   const double2* tab = cs2 + h;
 #pragma unroll
@@ -871,11 +877,15 @@ __device__ __forceinline__ void apply_cross(double (&xp)[B / 2], double (&xm)[B 
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       const double2 r = tab[t * B + 2 * j];
-      const double u = xp[j], v = xm[(j + t) & (H - 1)];
-      xp[j] = r.x * u - r.y * v;
-      xm[(j + t) & (H - 1)] = r.y * u + r.x * v;
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+        const double u = xp[n][j], v = xm[n][(j + t) & (H - 1)];
+        xp[n][j] = r.x * u - r.y * v;
+        xm[n][(j + t) & (H - 1)] = r.y * u + r.x * v;
+      }
     }
-    xm[t & (H - 1)] = __shfl_xor_sync(0xffffffffu, xm[t & (H - 1)], 1);
+#pragma unroll
+    for (int n = 0; n < NC; ++n) xm[n][t & (H - 1)] = __shfl_xor_sync(0xffffffffu, xm[n][t & (H - 1)], 1);
     if (SYNC) cta_bar();
   }
 }
@@ -883,7 +893,8 @@ __device__ __forceinline__ void apply_cross(double (&xp)[B / 2], double (&xm)[B 
 template <int B>
 __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
   using K = GG<B>;
-  constexpr int GR = K::R, GLD = K::LD, GJLD = K::JLD, H = K::H;
+  constexpr int GR = K::R, GLD = K::LD, GJLD = K::JLD, H = K::H, NC = K::NC;
+  constexpr int GAC = (GAT / 2) * NC;   // slab columns the register warps hold at a time
   const JqArgs& a = ga.j;
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
@@ -910,9 +921,10 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
   }
   __syncthreads();
   // static work assignment: Gram-update thread qt owns the quads qt, qt + 224, ... of the triangular enumeration
-  const bool is_quad = warp >= 1 && warp < 1 + GQT / 32;
-  const bool is_apply = warp >= GNW - GAT / 32;
-  const int qt = tid - 32, at = tid - (GNT - GAT), acol = at >> 1, ah = at & 1;
+  const bool is_quad = warp >= 1 && warp < 8 && warp != 4;
+  const bool is_apply = warp >= 9 && warp != 12;
+  const int qt = (warp - 1 - (warp > 4)) * 32 + lane;                 // 0 .. 191 on the Gram-update warps
+  const int at = (warp - 9 - (warp > 12)) * 32 + lane, acol = at >> 1, ah = at & 1;   // 0 .. 191 on the slab warps
   int qra[K::QPT], qcb[K::QPT];
   bool qok[K::QPT];
 #pragma unroll
@@ -943,6 +955,7 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
   unsigned target = 0;
   int sweeps = 0;
   int converged = (q < 2) ? 1 : 0;
+  long long pacc[8] = {};
   __syncthreads();
   for (int sw = 0; sw < a.max_sweeps && !converged; ++sw) {
     bool rotated = false;
@@ -954,33 +967,42 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
         else { bp = (R + slot) % (nbk - 1); bm = (R - slot + (nbk - 1)) % (nbk - 1); }
         auto grow = [&](int i) { return i < B ? bp * B + i : bm * B + (i - B); };
         const bool dbg = a.dbg && blockIdx.x == 0 && tid == 0;
-        long long tc = dbg ? clock64() : 0;
-        auto lap = [&](int slot_) { if (dbg) { long long n = clock64(); a.dbg[slot_] += n - tc; tc = n; } };
+        const bool dbg_all = a.dbg && tid == 0;   // every CTA: per-phase maximum / sum over the CTAs (skew behind the grid barrier)
+        long long tc = dbg_all ? clock64() : 0;
+        auto lap = [&](int slot_) {
+          if (dbg_all) { long long n = clock64(); if (dbg) a.dbg[slot_] += n - tc; pacc[slot_] += n - tc; tc = n; }
+        };
         // slab column of the register warps (cross rounds): requested now, used after the Gram / reduce phases
-        double xp[H], xm[H];
+        double xp[NC][H], xm[NC][H];
+        // lane pair `acol` holds the slab columns c0 + acol + n * (GAT / 2), n < NC
         auto col_of = [&](int c, int& gc) { gc = c < wR ? cR0 + c : cQ0 + (c - wR); return c < W && gc < (c < wR ? ndot : ld); };
-        auto col_load = [&](int gc, bool ok) {
+        auto col_load = [&](int c0) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
-            xp[j] = (ok && gp < q) ? __ldcg(a.Y + (size_t)gp * ld + gc) : 0.0;
-            xm[j] = (ok && gm < q) ? __ldcg(a.Y + (size_t)gm * ld + gc) : 0.0;
+          for (int n = 0; n < NC; ++n) {
+            int gc;
+            const bool ok = col_of(c0 + acol + n * (GAT / 2), gc);
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
+              xp[n][j] = (ok && gp < q) ? __ldcg(a.Y + (size_t)gp * ld + gc) : 0.0;
+              xm[n][j] = (ok && gm < q) ? __ldcg(a.Y + (size_t)gm * ld + gc) : 0.0;
+            }
           }
         };
-        auto col_store = [&](int gc, bool ok) {
+        auto col_store = [&](int c0) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
-            if (ok && gp < q) __stcg(a.Y + (size_t)gp * ld + gc, xp[j]);
-            if (ok && gm < q) __stcg(a.Y + (size_t)gm * ld + gc, xm[j]);
+          for (int n = 0; n < NC; ++n) {
+            int gc;
+            const bool ok = col_of(c0 + acol + n * (GAT / 2), gc);
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const int gp = grow(H * ah + j), gm = grow(B + H * ah + j);
+              if (ok && gp < q) __stcg(a.Y + (size_t)gp * ld + gc, xp[n][j]);
+              if (ok && gm < q) __stcg(a.Y + (size_t)gm * ld + gc, xm[n][j]);
+            }
           }
         };
-        bool xok = false;
-        int xgc = 0;
-        if (R >= 0 && is_apply) {
-          xok = col_of(acol, xgc);
-          col_load(xgc, xok);
-        }
+        if (R >= 0 && is_apply) col_load(0);
         // ---- 1. R-part slab load (cp.async, zero fill beyond the rank / the row length)
         {
           const int cpr = wR / 2;  // 16-byte chunks per slab row
@@ -1059,8 +1081,8 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
         if (!intra) {
           // ---- 5a. cross round: B steps; step t pairs row a (P) with row B + (a + t) mod B (M).  Per step ONE barrier:
           //   warp 0       rotations of step t + 1 from the buffer that step t reads (look-ahead through the bilinear form)
-          //   warps 1-7    G <- Rot G Rot^T, symmetric quads (statically assigned), upper triangle, buffer to buffer
-          //   warps 8-15   the rotations of step t on the slab columns, in registers
+          //   warps 1-3, 5-7    G <- Rot G Rot^T, symmetric quads (statically assigned), upper triangle, buffer to buffer
+          //   warps 9-11, 13-15   the rotations of step t on the slab columns, in registers
           // Every role runs its own branch-free loop (a taken branch costs the lone look-ahead warp an instruction fetch:
           // measured ~50 cycles each, ten of them per step in the first version of this loop).
           int anyrot = 0;
@@ -1077,9 +1099,9 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
           if (is_apply) {
             if (ga.skip & 6) {
               for (int st = 0; st < B; ++st) cta_bar();
-              if (ga.skip & 4) apply_cross<B, false>(xp, xm, ah, cs2);   // A/B: rotations applied after the loop
+              if (ga.skip & 4) apply_cross<B, NC, false>(xp, xm, ah, cs2);   // A/B: rotations applied after the loop
             } else {
-              apply_cross<B, true>(xp, xm, ah, cs2);
+              apply_cross<B, NC, true>(xp, xm, ah, cs2);
             }
           } else if (warp == 0) {
             // look-ahead: entries (lo, lo), (hi, hi), (lo, hi) of the NEXT matrix from the buffer step st reads,
@@ -1156,16 +1178,14 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
           lap(6);
           if (s_any) {
             rotated = true;
-            // ---- 6a. the register columns go straight back to global memory; slab columns beyond the 128 register columns
-            //          (chi = 512) are rotated afterwards from the complete table
+            // ---- 6a. the register columns go straight back to global memory; slab columns beyond the GAC register columns
+            //          are rotated afterwards from the complete table
             if (is_apply) {
-              col_store(xgc, xok);
+              col_store(0);
               for (int c0 = GAC; c0 < W; c0 += GAC) {   // warp-uniform trip count: the lane pairs exchange rows by shuffle
-                int gc;
-                const bool ok = col_of(c0 + acol, gc);
-                col_load(gc, ok);
-                apply_cross<B, false>(xp, xm, ah, cs2);
-                col_store(gc, ok);
+                col_load(c0);
+                apply_cross<B, NC, false>(xp, xm, ah, cs2);
+                col_store(c0);
               }
             }
           }
@@ -1263,6 +1283,17 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
     sweeps = sw + 1;
     if (ld_acquire(a.sync + 2 + sw) == 0u) converged = 1;
   }
+  if (a.dbg && tid == 0 && cid < nslots) {
+    long long busy = 0;
+    for (int k = 1; k < 8; ++k) {
+      busy += pacc[k];
+      atomicMax(reinterpret_cast<unsigned long long*>(a.dbg) + 16 + k, (unsigned long long)pacc[k]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 24 + k, (unsigned long long)pacc[k]);
+    }
+    atomicMax(reinterpret_cast<unsigned long long*>(a.dbg) + 16, (unsigned long long)busy);
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 24, (unsigned long long)busy);
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 15, 1ull);
+  }
   const int gw = blockIdx.x * GNW + warp;
   const int GW = gridDim.x * GNW;
   for (int i = gw; i < q; i += GW) {
@@ -1290,38 +1321,45 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
   }
 }
 
-// Launch: one cluster of 8 CTAs per block pair (cluster size 16 fits only 7 times on a B200: measured).
+// Launch: one cluster per block pair.  Cluster size 8 when the device holds one cluster per pair (15 fit on a B200: measured),
+// else 5 (24 or more fit; the Gram entries of the upper-triangular tiles must divide evenly: blocks of 16 rows only).
 template <int B>
-bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int kmax) {
+bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int r) {
   using K = GG<B>;
-  const int nbk = (((kmax + B - 1) / B) + 1) & ~1;
+  const int nbk = (((r + B - 1) / B) + 1) & ~1;
   const int nslots = nbk / 2;
   const int lq = a.ld - a.ndot;
-  const int cs = 8;
+  static DevOnce once;
+  static int maxcl[64][2] = {};
+  const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+  const int css[2] = {8, 5};
+  if (once.first(ctx->device)) {
+    QTT_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    for (int k = 0; k < 2; ++k) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(css[k] * 8);
+      cfg.blockDim = dim3(GNT);
+      cfg.dynamicSmemBytes = 200 * 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = css[k]; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, jacobi_gram_kernel<B>, &cfg) != cudaSuccess) n = 0;
+      (void)cudaGetLastError();
+      maxcl[dv][k] = n;
+    }
+  }
+  static const int cs_env = getenv("QTT_JACOBI_CS") ? atoi(getenv("QTT_JACOBI_CS")) : 0;
+  int ki = 0;
+  if (K::UTE % 5 == 0 && (K::UTE / 5) % 2 == 0 && (cs_env == 5 || (cs_env == 0 && nslots > maxcl[dv][0] && nslots <= maxcl[dv][1]))) ki = 1;
+  const int cs = css[ki];
+  if (maxcl[dv][ki] < 1) return false;
   const int wR = (((a.ndot + cs - 1) / cs) + 7) & ~7;
   const int wQ = (((lq + cs - 1) / cs) + 7) & ~7;
   const size_t smem = ((size_t)K::R * (wR + 4) + (size_t)K::R * K::JLD + (size_t)2 * K::R * K::LD) * sizeof(double);
   if (smem > 220 * 1024) return false;
-  static DevOnce once;
-  static int maxcl[64] = {};
-  const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
-  if (once.first(ctx->device)) {
-    QTT_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs * 8);
-    cfg.blockDim = dim3(GNT);
-    cfg.dynamicSmemBytes = 200 * 1024;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, jacobi_gram_kernel<B>, &cfg) != cudaSuccess) n = 0;
-    (void)cudaGetLastError();
-    maxcl[dv] = n;
-  }
-  if (maxcl[dv] < 1) return false;
-  const int ncl = nslots < maxcl[dv] ? nslots : maxcl[dv];
+  const int ncl = nslots < maxcl[dv][ki] ? nslots : maxcl[dv][ki];
   GjArgs ga;
   ga.j = a; ga.wR = wR; ga.wQ = wQ;
   ga.skip = getenv("QTT_GRAM_SKIP") ? atoi(getenv("QTT_GRAM_SKIP")) : 0;
@@ -1338,7 +1376,7 @@ bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int kmax) {
   cfg.attrs = at; cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, jacobi_gram_kernel<B>, ga);
   if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi_gram launch failed (%d clusters x %d): %s", ncl, cs, cudaGetErrorString(e));
-  if (a.dbg) fprintf(stderr, "[qtt trace]   gram jacobi B=%d: %d clusters x %d CTAs (max active %d), slab %d + %d columns, %zu B smem\n", B, ncl, cs, maxcl[dv], wR, wQ, smem);
+  if (a.dbg) fprintf(stderr, "[qtt trace]   gram jacobi B=%d: %d clusters x %d CTAs (max active %d / %d), slab %d + %d columns, %zu B smem\n", B, ncl, cs, maxcl[dv][0], maxcl[dv][1], wR, wQ, smem);
   ctx->launches++;
   return true;
 }
@@ -1349,7 +1387,7 @@ bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int kmax) {
 bool launch_jq_gram(Ctx* ctx, JqArgs& a, int r) {
   static const int bsel = getenv("QTT_JACOBI_B") ? atoi(getenv("QTT_JACOBI_B")) : 0;
   const int slots16 = ((((r + 15) / 16) + 1) & ~1) / 2;
-  if (bsel == 16 || (bsel == 0 && slots16 <= 15)) {
+  if (bsel == 16 || (bsel == 0 && slots16 <= 20)) {
     if (launch_jq_gram_b<16>(ctx, a, r)) return true;
   }
   return launch_jq_gram_b<32>(ctx, a, r);
@@ -1477,8 +1515,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   a.eigen_mode = eigen_mode ? 1 : 0;
   a.dbg = nullptr;
   if (ctx->profiling && getenv("QTT_TRACE") != nullptr) {
-    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(16));
-    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 128, ctx->stream));
+    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(32));
+    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 256, ctx->stream));
   }
   const int npairs = ((kmax + 1) & ~1) / 2;
   int grid = (npairs + 1) / 2;
@@ -1527,8 +1565,14 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     cudaEventElapsedTime(&ms, evq, evj);
     fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: numerical rank %d, jacobi %d sweeps %.3f ms (after QR)\n", q, p, h_info[3], h_info[1], ms);
     if (a.dbg) {
-      long long h[16];
-      cudaMemcpy(h, a.dbg, 128, cudaMemcpyDeviceToHost);
+      long long h[32];
+      cudaMemcpy(h, a.dbg, 256, cudaMemcpyDeviceToHost);
+      if (h[8] > 0 && h[15] > 0) {
+        const char* nm[8] = {"busy", "load", "gram", "csync1", "reduce", "check", "inner", "apply"};
+        fprintf(stderr, "[qtt trace]   per round over %lld CTAs, max / mean cycles:", h[15]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.0f / %.0f", nm[k], (double)h[16 + k] / h[8], (double)h[24 + k] / h[15] / h[8]);
+        fprintf(stderr, "\n");
+      }
       if (h[8] > 0)
         fprintf(stderr, "[qtt trace]   gram jacobi CTA0 cycles per round: barrier %.0f load %.0f gram %.0f csync1 %.0f reduce %.0f check %.0f inner %.0f apply %.0f (%lld rounds)\n",
                 (double)h[0] / h[8], (double)h[1] / h[8], (double)h[2] / h[8], (double)h[3] / h[8], (double)h[4] / h[8], (double)h[5] / h[8],
