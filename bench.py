@@ -10,10 +10,15 @@ Arnoldi steps = 31 effective-operator applications per bond; SURVEY.md section 7
 is needed for a well-defined sweeps/s).  Inputs are synthetic (numpy default_rng start vector, analytic operands).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job sweeps/s with the chains already resident in HBM, timed on the
-device (CUDA events recorded by the library on its own stream), max over ranks; `e2e` = the same through the public
+device (CUDA events recorded by the library on its own stream: they bracket the whole `linsolve(nsweeps=1)` call,
+environment build included), max over ranks; `e2e` = the SAME K sweeps from the SAME start state through the public
 API with HOST buffers (upload + sweep + download inside the timed region); `roofline` = the local matvec against the
-measured FP64 DMMA peak; `cpu_baseline` = the numpy/OpenBLAS oracle port on the host cores (bounded sample).
+measured FP64 DMMA peak; `cpu_baseline` = the numpy/OpenBLAS oracle port on the host cores (one full sweep).
+Protocol: the state after W warm-up sweeps is cloned; the device-resident leg and the host-buffer leg each run sweeps
+W+1 ... W+K chained from that clone (the per-sweep cost depends on the sweep index while the numerical rank of the
+state fills in, so both legs must cover the same sweeps); `ms_per_step_list` holds the per-sweep times of both.
 At N > 1 every rank solves an independent instance (wavenumber k_i): weak scaling, NCCL only gathers residuals.
+`--impl reference` times whole sweeps of the CPU port with every host core (thread count set explicitly).
 """
 import argparse
 import json
@@ -37,9 +42,14 @@ def bond_dims(n, chi):
     return [1] + [int(min(chi, 2 ** j, 2 ** (n - j))) for j in range(1, n)] + [1]
 
 
+def matvec2_flops(chil, chir, wl, wm, wr, d=2):
+    """F_mv of one two-site matvec, real FP64 (kept local: the reference arm must not load the GPU library)."""
+    return 2.0 * (chil * (wl * chil) * (d * d * chir) + (wl * d) * (chil * d * chir) * (wm * d)
+                  + (wm * d) * (chil * d * chir) * (wr * d) + (wr * chir) * (chil * d * d) * chir)
+
+
 def sweep_matvec_flops(n, chi, w, matvecs_per_bond):
     """Algorithmic FP64 flops of the matvecs of one sweep (SURVEY.md 8d formula with the actual edge bond dims)."""
-    from itensorqtt_jl_b200 import matvec2_flops
     d = bond_dims(n, chi)
     ws = [1] + [w] * (n - 1) + [1]
     per_bond = []
@@ -156,42 +166,48 @@ def run_ours(args):
     x = dx
     for i in range(args.warmup):
         x, info = step(x, canonical=True)   # random_mps() is right-orthonormal by construction
-    x_start = x.clone() if hasattr(x, "clone") else x
+    x_start = x.clone()   # both timed legs start from this state
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
     t0 = time.perf_counter()
-    dev_ms, infos = 0.0, []
+    dev_ms, infos, dev_list = 0.0, [], []
     for i in range(args.steps):
         x, info = step(x, canonical=True)
         dev_ms += info["device_ms"]
+        dev_list.append(float(info["device_ms"]))
         infos.append(info)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
     ms_per_step = dev_ms / max(args.steps, 1)
-    # ---- e2e (EVERY rank): host buffers -> upload -> one sweep -> download, through the public linsolve() call.
-    # The e2e input is the state the timed steps started from (same per-sweep work as `value`), downloaded once
-    # outside the timed region and re-homed in pinned memory.
+    # ---- e2e (EVERY rank): host buffers -> upload -> one sweep -> download, through the public linsolve() call, for the
+    # SAME K sweeps from the SAME start state as the device-resident leg (downloaded once outside the timed region and
+    # re-homed in pinned memory; every later step's input is the previous step's host result).
     hA, hb, hx = A, pinned_fortran_copy(b), pinned_fortran_copy(x_start.download())
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
+    e2e_steps = 0 if args.no_e2e else args.steps
     e2e_kw = dict(nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov, x0_canonical=True, ctx=ctx,
                   return_info=True, host_order="F")
     xo = hx
     if e2e_steps:
-        # one untimed pass of the same call: first-use costs of the host path (device blocks entering the caching
-        # allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
+        # one untimed pass of the same call on the start state: first-use costs of the host path (device blocks entering
+        # the caching allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
         q.linsolve(hA, hb, hx, -lam, 1.0, **e2e_kw)
     barrier()
+    e2e_list = []
     t0 = time.perf_counter()
     for i in range(e2e_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
         xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, **e2e_kw)
-        hx = xo   # chained like the device-resident steps: the e2e leg covers the same sweeps as `value`
+        e2e_list.append((time.perf_counter() - ts) * 1e3)
+        hx = xo
     barrier()
-    e2e_t = (time.perf_counter() - t0) / max(e2e_steps, 1)
+    e2e_t = (sum(e2e_list) / 1e3) / max(e2e_steps, 1)
     h2d = sum(c.nbytes for c in hA) + sum(c.nbytes for c in hb) + sum(c.nbytes for c in hx)
     d2h = sum(c.nbytes for c in xo)
     t = torch.tensor([ms_per_step, wall, float(infos[-1]["solver_resid"]), e2e_t], dtype=torch.float64, device="cuda")
@@ -209,6 +225,14 @@ def run_ours(args):
         return
     flops_sweep, _ = sweep_matvec_flops(n, chi, 3, args.krylov)
     value = world / (ms_max / 1e3)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the kernel pair from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "matvec_traffic.json")) as f:
+            tj = json.load(f)
+        if int(tj.get("chi", 0)) == chi:
+            traffic = float(tj["dram_bytes_per_matvec"])
+    except Exception:
+        traffic = None
     # ---- roofline of the local matvec (dominant work: 2 DMMA GEMM launches + 2 streaming kernels), live CUDA events
     rng = np.random.default_rng(0)
     L = rng.standard_normal((chi, 3, chi)); R = rng.standard_normal((chi, 3, chi))
@@ -220,10 +244,8 @@ def run_ours(args):
     sweep_mv_tflops = infos[-1]["flops_matvec"] / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the kernel pair from the round-1 `ncu --set full` capture
-                # (profiles/r01_ncu_full_matvec_cgs2.md: 3.70 MB + 7.88 MB read, 0 written, cold cache) -- algorithmic operand
-                # bytes 7.3 MB + the T2 intermediate (6.3 MB) that matvec_a hands to matvec_b through L2
-                "traffic": 11.58e6 if chi == 256 else None,
+                # from profiles/matvec_traffic.json (the ncu capture it was read from is named there); algorithmic operand bytes 7.3 MB
+                "traffic": traffic,
                 "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_kernel (L.v DMMA GEMM + W12 register epilogue) + "
                           "matvec_b_kernel (T2.R DMMA GEMM, in-CTA split-K), the pair timed back to back with CUDA events on "
                           "the library's stream" % chi,
@@ -244,71 +266,85 @@ def run_ours(args):
                    "bonds_per_sweep": 2 * (n - 1), "matvecs_per_sweep": int(infos[-1]["matvecs"]),
                    "instances": world, "instance_rule": "rank r solves wavenumber k_r = 2 pi (2^nk + r) from the same start vector",
                    "ms_per_step_per_rank": [float(v) for v in allt[:, 0]],
+                   "ms_per_step_list": {"device_resident_rank0": dev_list, "e2e_rank0": e2e_list},
+                   "protocol": "sweeps W+1..W+K chained from the state after W warm-up sweeps; the e2e leg repeats the same K sweeps "
+                               "from a clone of that state; device time = CUDA events around the whole linsolve(nsweeps=1) call, "
+                               "right-environment build included",
                    "l2": "256 MB buffer written between timed steps (L2 flush)",
                    "wall_s_timed_region": wall},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": ({"value": world / e2e_t, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d) * world,
                  "d2h_bytes_per_step": int(d2h) * world,
+                 "steps": e2e_steps,
                  "note": "upload of A, b, x (pinned host cores) + one sweep + download of x, per step, through "
                          "the public linsolve() call on every rank (barrier on both sides, max over ranks; bytes summed over "
-                         "ranks); the first x = the state the timed device-resident steps started from, then chained"}
+                         "ranks); the same K sweeps from the same start state as `value`"}
                 if e2e_steps else None),
         "roofline": roofline,
         "sweep": {"matvec_flops_per_sweep": flops_sweep, "maxlinkdim": int(infos[-1]["maxlinkdim"]),
                   "svd_sweeps_max": int(infos[-1]["svd_sweeps_max"]), "solver_resid_max_over_ranks": float(allt[:, 2].max())},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_sample(args, steps=1, warmup=0)
+        out["cpu_baseline"] = cpu_sweeps(args, max_sweeps=1, budget_s=40.0)
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_sample(args, steps, warmup):
-    """The oracle port (numpy tensordot -> OpenBLAS dgemm, LAPACK gesdd, KrylovKit-style GMRES) timed on the host cores
-    on a bounded sample: `m` consecutive full-size forward bond updates of the same workload, extrapolated to a sweep
-    by algorithmic matvec flops.  Used for `cpu_baseline` and for `--impl reference`."""
+def cpu_sweeps(args, max_sweeps, budget_s):
+    """The oracle port (numpy tensordot -> OpenBLAS dgemm, LAPACK gesdd, KrylovKit-style GMRES) timed on the host cores on
+    WHOLE two-site sweeps of the same workload (58 bond updates each at n = 30), chained from the random start like the GPU
+    arm.  The first sweep is always timed in full; further sweeps run while the projected total stays within `budget_s`.
+    The BLAS thread count is set explicitly to every host core (torchrun exports OMP_NUM_THREADS=1 to its workers).
+    Used for `cpu_baseline` (one sweep) and for `--impl reference`."""
     import oracle as O
+    cores = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_limits, threadpool_info
+        limiter = threadpool_limits(limits=cores)
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        threads = os.cpu_count() or 1
+        limiter, threads = None, cores
     n, chi = args.n, args.chi
     A = O.laplacian_mpo(n, 1.0)
     lam = -((2 * np.pi * (2.0 ** args.nk) / 2.0 ** n) ** 2)
     b = O.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
-    x0 = O.random_mps(n, chi, 2)
-    d = bond_dims(n, chi)
-    full = [j for j in range(n - 1) if d[j] == chi and d[j + 2] == chi]
-    j0 = full[0] if full else 0
-    m = max(1, min(args.cpu_bonds, len(full) if full else 1))
-    total, per_bond = sweep_matvec_flops(n, chi, 3, args.krylov)
-    weight = total / sum(per_bond[j0:j0 + m])
+    x = O.random_mps(n, chi, 2)
     times = []
-    for i in range(warmup + steps):
-        _, rec = O.linsolve(A, b, x0, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
-                            bond_window=(j0, m))
-        times.append(rec[0]["seconds"])  # the bond updates only; the window's environment set-up is not timed
-    t = float(np.mean(times[warmup:]))
-    return {"value": 1.0 / (t * weight), "unit": "sweeps/s", "cores": int(threads), "kind": "port",
-            "sample": "%d consecutive full-size (chi=%d) forward bond updates starting at bond %d (merge, %d matvecs + GMRES, "
-                      "SVD split, environment update) = %.2f s; extrapolated to one sweep by "
-                      "algorithmic matvec flops (x%.1f)" % (m, chi, j0 + 1, args.krylov + 1, t, weight),
-            "seconds_per_sample": t}
+    for i in range(max(1, max_sweeps)):
+        t0 = time.perf_counter()
+        x, rec = O.linsolve(A, b, x, -lam, 1.0, nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov)
+        times.append(time.perf_counter() - t0)
+        if sum(times) + times[-1] > budget_s:
+            break
+    del limiter
+    t = float(np.mean(times))
+    # the port is interpreter- and small-GEMM-bound: ~36 GFLOP/s of matvec work on 16 threads (a tuned C++/Julia CPU
+    # implementation would be a few times faster), so the GPU / CPU ratio is a generous one
+    flops, _ = sweep_matvec_flops(n, chi, 3, args.krylov)
+    return {"value": 1.0 / t, "unit": "sweeps/s", "cores": int(threads), "kind": "port",
+            "sample": "%d full sweep%s (2(n-1) = %d bond updates each: merge, %d matvecs + GMRES, SVD split, environment update), chained "
+                      "from the random start; mean %.2f s per sweep; matvec work alone = %.1f GFLOP/s (numpy-overhead-bound port)"
+                      % (len(times), "" if len(times) == 1 else "s", 2 * (n - 1), args.krylov + 1, t, flops / t / 1e9),
+            "seconds_per_sweep": t, "sweep_seconds": [float(v) for v in times]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_sample(args, steps=max(args.steps, 1), warmup=args.warmup)
+    cb = cpu_sweeps(args, max_sweeps=max(args.steps, 1), budget_s=args.cpu_budget)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "sweeps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_sample"] * 1e3, "higher_is_better": True,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_sweep"] * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]), CPU oracle port; the Julia reference cannot run "
-                                  "here (no julia toolchain, dependencies not vendored)" % (args.n, args.chi)},
+           "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]): laplacian_mpo w=3, a0=-lambda (nk=%d), "
+                                  "maxdim=mindim=%d, cutoff=0, fixed-work GMRES %d Arnoldi steps/bond; CPU oracle port (the Julia "
+                                  "reference cannot run here: no julia toolchain, dependencies not vendored)"
+                                  % (args.n, args.chi, args.nk, args.chi, args.krylov),
+                      "timed_sweeps": len(cb["sweep_seconds"]),
+                      "protocol": "whole sweeps chained from the random start, no warm-up (LAPACK gesdd cost does not depend on the "
+                                  "numerical rank); as many of --steps as fit --cpu-budget seconds"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -324,7 +360,7 @@ def main():
     ap.add_argument("--chi", type=int, default=CHI)
     ap.add_argument("--nk", type=int, default=NK)
     ap.add_argument("--krylov", type=int, default=KRYLOV)
-    ap.add_argument("--cpu-bonds", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU sweeps the reference arm may time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list runs)")
     ap.add_argument("--roofline-reps", type=int, default=200)

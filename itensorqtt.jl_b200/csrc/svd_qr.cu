@@ -42,6 +42,11 @@ struct QrCtl {
   int serial;   // panel serial number
   double F2;    // |Z|_F^2
   double thr;   // zero threshold on squared norms
+  // block Gram-Schmidt variant (gs_* kernels)
+  int r_next;   // r after the panel in flight
+  int nsel;     // rows selected for the panel in flight
+  int sel[32];  // their indices
+  int rj;       // rows of Y with a non-zero R part (the rows Jacobi rotates; 0 = all r rows).  Completion rows follow them.
 };
 
 // SE rows [0,q) = Z (zero padded to ldp), rows [q, q+p) = identity; norms[i] = |z_i|^2
@@ -73,7 +78,7 @@ __global__ void qr_init_kernel(const double* __restrict__ M, int q, int p, int l
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctl->r = 0; ctl->done = 0; ctl->nbp = 0; ctl->serial = 0; ctl->F2 = -1.0; ctl->thr = 0.0;
+    ctl->r = 0; ctl->done = 0; ctl->nbp = 0; ctl->serial = 0; ctl->F2 = -1.0; ctl->thr = 0.0; ctl->rj = 0;
   }
 }
 
@@ -944,7 +949,8 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
     gti[u] = ti; gtj[u] = ti + rem;
   }
 
-  const int q = a.ctl->r;
+  const int qall = a.ctl->r;                               // rows of Y (sorted / gathered at the end)
+  const int q = a.ctl->rj > 0 ? a.ctl->rj : qall;          // rows with a non-zero R part: the ones that are rotated
   const double thr = a.ctl->thr;
   const double tol2 = a.tol * a.tol;
   const int nbk = (((q + B - 1) / B) + 1) & ~1;
@@ -1296,7 +1302,7 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
   }
   const int gw = blockIdx.x * GNW + warp;
   const int GW = gridDim.x * GNW;
-  for (int i = gw; i < q; i += GW) {
+  for (int i = gw; i < qall; i += GW) {
     const double* ri = a.Y + (size_t)i * a.ld;
     double acc = 0.0;
     for (int col = 2 * lane; col < a.ndot; col += 64) {
@@ -1304,19 +1310,19 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
       acc += v.x * v.x + v.y * v.y;
     }
     acc = warp_sum(acc);
-    if (!(acc > thr)) acc = 0.0;
+    if (!(acc > thr) || i >= q) acc = 0.0;
     if (a.eigen_mode) acc = sqrt(acc);
     if (lane == 0) __stcg(a.norms + i, acc);
   }
   grid_sync(a.sync, target);
-  dev::rank_sort_desc(a.norms, q, a.kmax, a.sig2, a.perm);
+  dev::rank_sort_desc(a.norms, qall, a.kmax, a.sig2, a.perm);
   grid_sync(a.sync, target);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double err;
     a.info[0] = dev::truncate_spectrum(a.sig2, a.kmax, a.cutoff, a.maxdim, a.mindim, &err);
     a.info[1] = sweeps;
     a.info[2] = converged;
-    a.info[3] = q;
+    a.info[3] = qall;
     a.derr[0] = err;
   }
 }
@@ -1393,6 +1399,443 @@ bool launch_jq_gram(Ctx* ctx, JqArgs& a, int r) {
   return launch_jq_gram_b<32>(ctx, a, r);
 }
 
+// ------------------------------------------------------------------ rank-revealing QR, second generation: block Gram-Schmidt
+// The Householder panels above are one CTA working through 32 dependent reflectors (4.4 us each: 140 us per panel,
+// 2.8 ms for a full-rank 512 x 512 tensor).  Here the orthonormal basis Q of the row space is built explicitly, 32 rows
+// per panel, and everything but a 32 x 32 Cholesky factor runs on the DMMA core:
+//   select    the <= 32 unprocessed rows with the largest residual norm above the zero threshold (as before);
+//   reorth    P <- P - (P Q^T) Q against ALL earlier basis rows (second Gram-Schmidt pass: two DMMA GEMMs);
+//   panel     CholeskyQR of the diagonally scaled panel: Gram matrix (DMMA), Cholesky with deferral (a row whose pivot
+//             falls below 1e-6 of its own squared norm is left for a later panel, so the panel stays well conditioned),
+//             Q1 = L^-1 D^-1 P (DMMA), then one Newton-Schulz step Q1 <- (1.5 I - 0.5 Q1 Q1^T) Q1 (orthogonality ~1e-9 -> eps);
+//   update    coefficients C = Q1 Zw^T of every remaining row (they ARE the rows of R) and Zw <- Zw - C^T Q1 (two DMMA GEMMs),
+//             fresh residual norms.
+// Y = [R | Q^T] is written directly (no build_y transpose).  The factorisation stops at the numerical rank like the
+// Householder variant.  Basis rows beyond the rank (needed only when `mindim` exceeds it) are not produced: the caller
+// falls back to the Householder variant, whose accumulated Q supplies the orthonormal completion.
+constexpr int GSB = 32;           // panel height
+constexpr int GST = 512;          // threads of the panel kernel
+constexpr double GS_DEFER = 1e-6; // pivot threshold relative to the row's own squared norm
+
+__global__ void gs_init_kernel(const double* __restrict__ M, int q, int p, int ldp, double* __restrict__ Zw, double* __restrict__ norms,
+                               int* __restrict__ rowstate, QrCtl* ctl) {
+  dev::pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int GW = (gridDim.x * blockDim.x) >> 5;
+  for (int i = gw; i < q; i += GW) {
+    const double* src = M + (size_t)i * p;
+    double* dst = Zw + (size_t)i * ldp;
+    double acc = 0.0;
+    for (int c = lane; c < ldp; c += 32) {
+      const double v = c < p ? src[c] : 0.0;
+      dst[c] = v;
+      acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { norms[i] = acc; rowstate[i] = 0; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->r = 0; ctl->done = 0; ctl->nbp = 0; ctl->serial = 0; ctl->F2 = -1.0; ctl->thr = 0.0; ctl->r_next = 0; ctl->nsel = 0; ctl->rj = 0;
+  }
+}
+
+// One CTA per panel slot: every CTA repeats the (cheap, deterministic) selection, CTA u copies row sel[u] into Pbuf[u].
+// (`first`: the zero threshold is derived from the initial norms by every CTA itself; no CTA reads what another one writes here.)
+// thr_fixed > 0 (completion phase): that threshold instead of the one derived from |Z|_F.
+__global__ void __launch_bounds__(256) gs_select_kernel(const double* __restrict__ Zw, int q, int p, int ldp, int rmax, double zero_tol2,
+                                                        int first, double thr_fixed, const double* __restrict__ norms,
+                                                        const int* __restrict__ rowstate, double* __restrict__ Pbuf, QrCtl* ctl) {
+  dev::pdl_wait();
+  extern __shared__ double cand[];   // [q] residual norm of the unprocessed rows, -1 otherwise
+  __shared__ int sel[GSB];
+  __shared__ double red[8];
+  __shared__ double s_thr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int u = blockIdx.x;
+  double* prow = Pbuf + (size_t)u * ldp;
+  const int r0 = ctl->r_next;
+  if (ctl->done) {
+    for (int c = tid; c < ldp; c += 256) prow[c] = 0.0;
+    return;
+  }
+  double thr = thr_fixed > 0.0 ? thr_fixed : (first ? 0.0 : ctl->thr);
+  if (first && !(thr_fixed > 0.0)) {   // |Z|_F^2 once (the initial norms are the full row norms); same summation order in every CTA
+    double acc = 0.0;
+    for (int i = tid; i < q; i += 256) acc += norms[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int k = 0; k < 8; ++k) sum += red[k];
+      s_thr = zero_tol2 * sum;
+      if (u == 0) { ctl->F2 = sum; ctl->thr = s_thr; }
+    }
+    __syncthreads();
+    thr = s_thr;
+  }
+  int want = rmax - r0;
+  if (want > GSB) want = GSB;
+  if (tid < GSB) sel[tid] = -1;
+  for (int i = tid; i < q; i += 256) cand[i] = (rowstate[i] == 0) ? norms[i] : -1.0;
+  __syncthreads();
+  for (int i = tid; i < q; i += 256) {
+    const double ni = cand[i];
+    if (!(ni > thr)) continue;
+    int rank = 0;
+    for (int j = 0; j < q; ++j) {
+      const double nj = cand[j];
+      rank += (nj > ni) || (nj == ni && j < i);
+    }
+    if (rank < want) sel[rank] = i;   // ranks are distinct and dense among the rows above the threshold
+  }
+  __syncthreads();
+  const int mine = sel[u];
+  for (int c = tid; c < ldp; c += 256) prow[c] = mine >= 0 ? Zw[(size_t)mine * ldp + c] : 0.0;
+  if (u == 0 && tid == 0) {
+    int nsel = 0;
+    for (int k = 0; k < GSB; ++k) {
+      ctl->sel[k] = sel[k];
+      nsel += sel[k] >= 0;
+    }
+    ctl->r = r0;
+    ctl->nsel = nsel;
+    ctl->nbp = 0;
+  }
+}
+
+// CholeskyQR + Newton-Schulz of the (re-orthogonalised) panel Pbuf: accepted rows become new orthonormal basis rows, written
+// (compacted, zero rows behind them); the panel rows go back to Zw so that the update GEMMs see them.
+__global__ void __launch_bounds__(GST) gs_panel_kernel(const double* __restrict__ Pbuf, int p, int ldp, int pld, int rmax,
+                                                       double* __restrict__ Zw, int* __restrict__ rowstate, double* __restrict__ Yq, int ldy,
+                                                       double thr_fixed, QrCtl* ctl, long long* dbg) {
+  dev::pdl_wait();
+  long long tph = dbg ? clock64() : 0;
+  auto lap = [&](int k) { if (dbg && threadIdx.x == 0) { const long long n = clock64(); dbg[k] += n - tph; tph = n; } };
+  extern __shared__ __align__(16) double psm[];
+  double* P = psm;                          // [GSB][pld]
+  double* Gs = P + (size_t)GSB * pld;       // [GSB][GSB + 1] scaled Gram matrix, then L
+  double* T = Gs + GSB * (GSB + 1);         // [GSB][GSB + 4] compacted L^-1 D^-1, then the Newton-Schulz matrix
+  __shared__ double dn[GSB], sc[GSB], invd[GSB];
+  __shared__ int acc[GSB], slot[GSB];
+  __shared__ int s_na;
+  constexpr int TLD = GSB + 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bool done = ctl->done != 0;
+  const int nsel = done ? 0 : ctl->nsel;
+  if (nsel == 0) {   // nothing above the zero threshold is left (or the basis is complete): the update kernel becomes a no-op
+    if (tid == 0) { ctl->done = 1; ctl->nbp = 0; }
+    return;
+  }
+  const int r0 = ctl->r;
+  const double thr = thr_fixed > 0.0 ? thr_fixed : ctl->thr;
+  // ---- load; the re-orthogonalised rows replace the working rows
+  {
+    const int cpr = ldp / 2;
+    for (int e = tid; e < GSB * cpr; e += GST) {
+      const int u = e / cpr, c = (e - u * cpr) * 2;
+      cp_async16(P + (size_t)u * pld + c, Pbuf + (size_t)u * ldp + c, 16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    for (int e = tid; e < GSB * (pld - ldp); e += GST) P[(size_t)(e / (pld - ldp)) * pld + ldp + e % (pld - ldp)] = 0.0;
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    if (tid < GSB) slot[tid] = ctl->sel[tid];   // (slot[] is reused: the row indices of the panel)
+    __syncthreads();
+    for (int e = tid; e < GSB * cpr; e += GST) {   // the working rows take the re-orthogonalised values
+      const int u = e / cpr, c = (e - u * cpr) * 2;
+      const int i = slot[u];
+      if (i >= 0) *reinterpret_cast<double2*>(Zw + (size_t)i * ldp + c) = *reinterpret_cast<const double2*>(P + (size_t)u * pld + c);
+    }
+  }
+  lap(0);
+  // ---- squared norms and scales
+  for (int u = warp; u < GSB; u += GST / 32) {
+    const double* row = P + (size_t)u * pld;
+    double a = 0.0;
+    for (int c = lane; c < p; c += 32) a += row[c] * row[c];
+    a = warp_sum(a);
+    if (lane == 0) {
+      dn[u] = a;
+      sc[u] = (u < nsel && a > thr) ? rsqrt(a) : 0.0;
+    }
+  }
+  __syncthreads();
+  // ---- Gram matrix on the DMMA core: warp w -> 8 x 8 tile (w / 4, w % 4), four interleaved accumulators along K
+  auto gram = [&](bool scaled) {
+    if (warp >= 10) return;   // the 10 tiles of the upper triangle (the FP64 rate of ONE SM is what this kernel is bound by)
+    int ti = 0, rem = warp;
+    while (rem >= 4 - ti) { rem -= 4 - ti; ++ti; }
+    const int tj = ti + rem;
+    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* pa = P + (size_t)(ti * 8 + g) * pld + t4;
+    const double* pb = P + (size_t)(tj * 8 + g) * pld + t4;
+    int k0 = 0;
+    for (; k0 + 16 <= pld; k0 += 16) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dmma884(a0[v], a1[v], pa[k0 + 4 * v], pb[k0 + 4 * v]);
+    }
+    for (; k0 < pld; k0 += 4) dmma884(a0[0], a1[0], pa[k0], pb[k0]);
+    const double v0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), v1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    const int i = ti * 8 + g, j = tj * 8 + 2 * t4;
+    const double si = scaled ? sc[i] : 1.0;
+    const double w0 = v0 * si * (scaled ? sc[j] : 1.0), w1 = v1 * si * (scaled ? sc[j + 1] : 1.0);
+    Gs[i * (GSB + 1) + j] = w0;
+    Gs[i * (GSB + 1) + j + 1] = w1;
+    Gs[j * (GSB + 1) + i] = w0;
+    Gs[(j + 1) * (GSB + 1) + i] = w1;
+  };
+  lap(1);
+  gram(true);
+  __syncthreads();
+  lap(2);
+  // ---- Cholesky with deferral, all 512 threads: thread e owns the entries (i, j) = (e / 32, e % 32) and (i + 16, j) of the
+  //      32 x 32 matrix.  Right-looking, ONE barrier per step: the trailing update uses the unscaled column,
+  //      G[i][j] -= G[i][t] G[j][t] / piv, and the scaled column L[i][t] = G[i][t] / sqrt(piv) goes to a separate array.
+  //      (A single warp working through the 496 dependent dot products took 41 000 cycles per panel: measured.)
+  {
+    constexpr int LD = GSB + 1;
+    double* Lm = T + GSB * TLD;          // [32][33] the Cholesky factor (zero columns for deferred / null rows)
+    const int j = tid & 31, i0 = tid >> 5, i1 = i0 + 16;
+    for (int t = 0; t < GSB; ++t) {
+      const double piv = Gs[t * LD + t];
+      const bool ok = sc[t] > 0.0 && piv > GS_DEFER;
+      const double inv = ok ? rsqrt(piv) : 0.0, inv2 = inv * inv;
+      const double gjt = Gs[j * LD + t];
+      const double g0 = Gs[i0 * LD + t], g1 = Gs[i1 * LD + t];
+      if (j == t) {
+        Lm[i0 * LD + t] = i0 >= t ? g0 * inv : 0.0;
+        Lm[i1 * LD + t] = i1 >= t ? g1 * inv : 0.0;
+        if (i0 == 0) { invd[t] = inv; acc[t] = ok ? 1 : 0; }
+      }
+      __syncthreads();   // every thread has read column t before anybody overwrites entries of later columns it may need
+      if (j > t) {
+        if (i0 > t) Gs[i0 * LD + j] -= g0 * gjt * inv2;
+        if (i1 > t) Gs[i1 * LD + j] -= g1 * gjt * inv2;
+      }
+      __syncthreads();
+    }
+    // ---- X = L^-1 (forward substitution on all 32 columns at once): thread owns X[i0][j], X[i1][j] and the running sums
+    double s0 = 0.0, s1 = 0.0;
+    double* X = Gs;                      // Gs is free now
+    for (int t = 0; t < GSB; ++t) {
+      // row t of X is final once the sums of steps < t are in: x[t][j] = (delta_tj - s[t][j]) invd[t]
+      if (i0 == t) X[t * LD + j] = (((t == j && acc[j]) ? 1.0 : 0.0) - s0) * invd[t];
+      if (i1 == t) X[t * LD + j] = (((t == j && acc[j]) ? 1.0 : 0.0) - s1) * invd[t];
+      __syncthreads();
+      const double xt = X[t * LD + j];
+      if (i0 > t) s0 += Lm[i0 * LD + t] * xt;
+      if (i1 > t) s1 += Lm[i1 * LD + t] * xt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int na = 0;
+      for (int t = 0; t < GSB; ++t) { slot[t] = na; na += acc[t]; }
+      s_na = na;
+    }
+    __syncthreads();
+    // T = compacted rows of X, columns scaled: T[slot(t)][c] = X[t][c] sc[c]; rows beyond na are zero
+    const double x0v = X[i0 * LD + j], x1v = X[i1 * LD + j];
+    __syncthreads();   // X (= Gs) and Lm (behind T) are both dead after this point; T itself is written next
+    for (int e = tid; e < GSB * TLD; e += GST) T[e] = 0.0;
+    __syncthreads();
+    if (acc[i0]) T[slot[i0] * TLD + j] = x0v * sc[j];
+    if (acc[i1]) T[slot[i1] * TLD + j] = x1v * sc[j];
+  }
+  __syncthreads();
+  lap(3);
+  const int na = s_na;
+  // ---- rows <- T rows (32 x 32 times 32 x p on the DMMA core; a warp owns 8-column strips, so P is updated in place)
+  auto apply_t = [&]() {
+    for (int strip = warp; strip < pld / 8; strip += GST / 32) {
+      const int n0 = strip * 8;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k0 = 0; k0 < GSB; k0 += 4) {
+        const double bv = P[(size_t)(k0 + t4) * pld + n0 + g];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) dmma884(a0[mt], a1[mt], T[(mt * 8 + g) * TLD + k0 + t4], bv);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) *reinterpret_cast<double2*>(P + (size_t)(mt * 8 + g) * pld + n0 + 2 * t4) = make_double2(a0[mt], a1[mt]);
+    }
+  };
+  apply_t();
+  __syncthreads();
+  lap(4);
+  // ---- one Newton-Schulz step: Q1 <- (1.5 I - 0.5 Q1 Q1^T) Q1
+  gram(false);
+  __syncthreads();
+  lap(5);
+  for (int e = tid; e < GSB * GSB; e += GST) {
+    const int i = e / GSB, j = e % GSB;
+    T[i * TLD + j] = (i < na && j < na) ? ((i == j ? 1.5 : 0.0) - 0.5 * Gs[i * (GSB + 1) + j]) : 0.0;
+  }
+  __syncthreads();
+  apply_t();
+  __syncthreads();
+  lap(6);
+  // ---- results: the new basis rows go straight into the carried part of Y = [R | Q^T] (rows r0 ... r0 + na - 1)
+  for (int e = tid; e < na * (ldp / 2); e += GST) {
+    const int u = e / (ldp / 2), c = (e % (ldp / 2)) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (c < p) v = *reinterpret_cast<const double2*>(P + (size_t)u * pld + c);
+    *reinterpret_cast<double2*>(Yq + (size_t)(r0 + u) * ldy + c) = v;
+  }
+  if (tid < GSB && tid < nsel) {
+    const int i = ctl->sel[tid];
+    if (i >= 0 && (acc[tid] || !(dn[tid] > thr))) rowstate[i] = 1;   // accepted, or numerically in the span already
+  }
+  lap(7);
+  if (tid == 0) {
+    if (dbg) dbg[8] += 1;
+    ctl->nbp = na;
+    ctl->r_next = r0 + na;
+    ctl->serial = ctl->serial + 1;
+    if (r0 + na >= rmax) ctl->done = 1;
+  }
+}
+
+// Right-looking update of the working rows against the panel's basis rows Q1 (<= 32, in shared memory):
+//   c_t = z_i . q_t (all t from the same z_i: the rows of Q1 are orthonormal to rounding), z_i <- z_i - sum_t c_t q_t,
+// the new residual norm, and the coefficients straight into Y[r0 + t][i] (rows of R).  A warp owns TWO rows at a time so that every
+// shared-memory load of Q1 feeds two FMAs.  Replaces two latency-bound skinny GEMMs (K = 512 on 16 tiles: 14 us each).
+template <int NPL>
+__global__ void __launch_bounds__(256) gs_update_kernel(double* __restrict__ Zw, int q, int p, int ldp, const int* __restrict__ rowstate,
+                                                        double* __restrict__ norms, double* __restrict__ Y, int qd, int ldy, int write_r,
+                                                        const QrCtl* ctl) {
+  dev::pdl_wait();
+  extern __shared__ __align__(16) double qsm[];   // [na rounded up to 4][ldp]
+  const int na = ctl->nbp;
+  if (na == 0) return;
+  const int r0 = ctl->r;
+  const int na4 = (na + 3) & ~3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {   // stage the basis rows: all copies in flight at once (a load loop through registers was latency-bound: 16 us of 50)
+    const int cpr = ldp / 2;
+    for (int e = tid; e < na4 * cpr; e += 256) {
+      const int t = e / cpr, c = (e - t * cpr) * 2;
+      const bool ok = t < na;
+      cp_async16(qsm + (size_t)t * ldp + c, ok ? Y + (size_t)(r0 + t) * ldy + qd + c : Y, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+  }
+  const int npairs = (q + 1) / 2;
+  for (int pr = blockIdx.x * 8 + warp; pr < npairs; pr += gridDim.x * 8) {
+    const int i0 = 2 * pr, i1 = 2 * pr + 1;
+    const bool ok1 = i1 < q;
+    double x0[NPL], x1[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const int c = lane + 32 * k;
+      x0[k] = c < p ? Zw[(size_t)i0 * ldp + c] : 0.0;
+      x1[k] = (ok1 && c < p) ? Zw[(size_t)i1 * ldp + c] : 0.0;
+    }
+    double c0 = 0.0, c1 = 0.0;   // lane t keeps the coefficients of basis row t
+    for (int t = 0; t < na4; t += 4) {   // four basis rows at a time: eight interleaved warp reductions
+      double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ldp) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const double w = qsm[(size_t)(t + v) * ldp + c];
+            d0[v] += x0[k] * w;
+            d1[v] += x1[k] * w;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          d0[v] += __shfl_xor_sync(0xffffffffu, d0[v], o);
+          d1[v] += __shfl_xor_sync(0xffffffffu, d1[v], o);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (lane == t + v) { c0 = d0[v]; c1 = d1[v]; }
+    }
+    for (int t = 0; t < na4; t += 4) {
+      double e0[4], e1[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        e0[v] = __shfl_sync(0xffffffffu, c0, t + v);
+        e1[v] = __shfl_sync(0xffffffffu, c1, t + v);
+      }
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ldp) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const double w = qsm[(size_t)(t + v) * ldp + c];
+            x0[k] -= e0[v] * w;
+            x1[k] -= e1[v] * w;
+          }
+        }
+      }
+    }
+    double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < p) {
+        Zw[(size_t)i0 * ldp + c] = x0[k];
+        if (ok1) Zw[(size_t)i1 * ldp + c] = x1[k];
+      }
+      n0 += x0[k] * x0[k];
+      n1 += x1[k] * x1[k];
+    }
+    n0 = warp_sum(n0);
+    n1 = warp_sum(n1);
+    if (write_r && lane < na) {   // rows of R: Y[r0 + t][i] = z_i . q_t
+      Y[(size_t)(r0 + lane) * ldy + i0] = c0;
+      if (ok1) Y[(size_t)(r0 + lane) * ldy + i1] = c1;
+    }
+    if (lane == 0) {
+      if (rowstate[i0] == 0) norms[i0] = n0;
+      if (ok1 && rowstate[i1] == 0) norms[i1] = n1;
+    }
+  }
+}
+
+__global__ void gs_commit_kernel(QrCtl* ctl, int reopen) {
+  dev::pdl_wait();
+  if (threadIdx.x == 0) {
+    ctl->r = ctl->r_next;
+    if (reopen) { ctl->done = 0; ctl->nsel = 0; ctl->nbp = 0; ctl->rj = ctl->r_next; }
+  }
+}
+
+// Completion phase (`mindim` asks for more basis rows than the numerical rank): the working matrix is the projector
+// I - Q^T Q, whose rows are the coordinate vectors with the span of Q removed.  Zw2 arrives holding -Q^T Q (DMMA GEMM).
+__global__ void gs_projector_kernel(double* __restrict__ Zw2, int p, int ldp, double* __restrict__ norms2, int* __restrict__ rowstate2) {
+  dev::pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int GW = (gridDim.x * blockDim.x) >> 5;
+  for (int i = gw; i < p; i += GW) {
+    double* row = Zw2 + (size_t)i * ldp;
+    double a = 0.0;
+    for (int c = lane; c < ldp; c += 32) {
+      double v = c < p ? row[c] : 0.0;
+      if (c == i) v += 1.0;
+      row[c] = v;
+      a += v * v;
+    }
+    a = warp_sum(a);
+    if (lane == 0) { norms2[i] = a; rowstate2[i] = 0; }
+  }
+}
+
 // Wn[i][:] = carried (Q^T) part of row perm[i].  Positions beyond the numerical rank r (sigma = 0, kept only because of
 // `mindim`) receive the orthonormal completion LAPACK's SVD would return there: column i of the accumulated Q (the identity
 // block of SE), which is orthogonal to the first r columns.  A zero row instead would make the next bond's projected
@@ -1448,8 +1891,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   int* inpanel = reinterpret_cast<int*>(ctx->arena.alloc(q / 2 + 1));
   double* Vp = ctx->arena.alloc((size_t)NB * ldp);
   double* taus = ctx->arena.alloc(NB);
-  QrCtl* ctl = reinterpret_cast<QrCtl*>(ctx->arena.alloc(8));
-  double* Y = ctx->arena.alloc((size_t)kmax * ldy);
+  QrCtl* ctl = reinterpret_cast<QrCtl*>(ctx->arena.alloc(64));
+  double* Y = ctx->arena.alloc((size_t)(kmax + GSB) * ldy);
   double* sig2 = ctx->arena.alloc(kmax);
   int* perm = reinterpret_cast<int*>(ctx->arena.alloc(kmax / 2 + 1));
   int* info = reinterpret_cast<int*>(ctx->arena.alloc(4));
@@ -1460,7 +1903,124 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   // |row| itself and the reference's cutoffs go down to 1e-15: the floor is kept as low as the rotation noise allows
   // (same rule as svd_rows_ex).
   const double zt = (eigen_mode ? 2.0 : 8.0) * tol;
-  {
+  const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
+  cudaEvent_t evq0 = nullptr;
+  if (trace) { cudaEventCreate(&evq0); cudaEventRecord(evq0, ctx->stream); }
+  // ---- block Gram-Schmidt QR (DMMA); falls through to the Householder panels when it does not apply
+  static const bool gs_off = getenv("QTT_QR") != nullptr && std::string(getenv("QTT_QR")) == "householder";
+  const int pld = ldp + ((4 - ldp % 16) + 16) % 16;
+  const size_t gs_smem = ((size_t)GSB * pld + 2 * GSB * (GSB + 1) + GSB * (GSB + 4)) * sizeof(double);
+  int need = mindim < kmax ? mindim : kmax;   // basis rows the truncation rule may keep whatever the spectrum
+  bool gs_done = false;
+  if (!gs_off && p % 2 == 0 && kmax >= 64 && gs_smem <= 220 * 1024) {
+    static DevOnce gs_once;
+    if (gs_once.first(ctx->device)) {
+      set_smem(gs_panel_kernel, 220 * 1024);
+      set_smem(gs_update_kernel<8>, 200 * 1024);
+      set_smem(gs_update_kernel<16>, 200 * 1024);
+      set_smem(gs_update_kernel<24>, 200 * 1024);
+    }
+    double* Zw = SE;   // the (q + p) x ldp Householder workspace is free on this path
+    double* Pbuf = ctx->arena.alloc((size_t)GSB * ldp);
+    double* C2 = ctx->arena.alloc((size_t)(kmax + GSB) * GSB);
+    QTT_CUDA(cudaMemsetAsync(Y, 0, sizeof(double) * (size_t)(kmax + GSB) * ldy, ctx->stream));
+    {
+      int grid = (q + 7) / 8;
+      if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
+      launch_pdl(ctx, "gs_init", gs_init_kernel, dim3(grid), dim3(256), 0, M, q, p, ldp, Zw, norms, rowstate, ctl);
+    }
+    long long* gs_dbg = nullptr;
+    if (trace) {
+      gs_dbg = reinterpret_cast<long long*>(ctx->arena.alloc(16));
+      QTT_CUDA(cudaMemsetAsync(gs_dbg, 0, 128, ctx->stream));
+    }
+    int* h_done = reinterpret_cast<int*>(ctx->h_scal + 17);
+    // panels over the working rows W (nrows x ldp) until `rmax` basis rows exist or nothing above the threshold is left
+    auto run_panels = [&](double* W, int nrows, double* nrm, int* rst, int rmax, int r_have, bool main_phase, double thr_fixed) -> bool {
+      const int nominal = (rmax - r_have + GSB - 1) / GSB;
+      for (int pn = 0; pn < nominal + 16; ++pn) {
+        launch_pdl(ctx, "gs_select", gs_select_kernel, dim3(GSB), dim3(256), sizeof(double) * nrows, (const double*)W, nrows, p, ldp, rmax, zt * zt,
+                   (main_phase && pn == 0) ? 1 : 0, thr_fixed, (const double*)nrm, (const int*)rst, Pbuf, ctl);
+        if (pn > 0 || r_have > 0) {
+          int J = r_have + pn * GSB;   // upper bound of the basis rows so far (rows beyond r are zero)
+          if (J > kmax) J = kmax;
+          GemmDesc g1;   // C2 (J x 32) = Q (J x p) . Pbuf^T
+          g1.A = Y + qd; g1.B = Pbuf; g1.C = C2; g1.transB = true;
+          g1.M = J; g1.N = GSB; g1.K = p; g1.lda = ldy; g1.ldb = ldp; g1.ldc = GSB;
+          gemm(ctx, g1);
+          GemmDesc g2;   // Pbuf (32 x p) -= C2^T . Q
+          g2.A = C2; g2.B = Y + qd; g2.C = Pbuf; g2.transA = true;
+          g2.M = GSB; g2.N = p; g2.K = J; g2.lda = GSB; g2.ldb = ldy; g2.ldc = ldp; g2.alpha = -1.0; g2.beta = 1.0;
+          gemm(ctx, g2);
+        }
+        launch_pdl(ctx, "gs_panel", gs_panel_kernel, dim3(1), dim3(GST), gs_smem, (const double*)Pbuf, p, ldp, pld, rmax, W, rst, Y + qd, ldy, thr_fixed, ctl,
+                   gs_dbg);
+        {   // coefficients of every row on the new basis rows (= rows of R), W <- W - C^T Q1, fresh residual norms
+          int ug = ((nrows + 1) / 2 + 7) / 8;
+          if (ug > ctx->sms) ug = ctx->sms;
+          const size_t usm = sizeof(double) * (size_t)GSB * ldp;
+          const int wr = main_phase ? 1 : 0;
+          if (ldp <= 256) launch_pdl(ctx, "gs_update", gs_update_kernel<8>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
+          else if (ldp <= 512) launch_pdl(ctx, "gs_update", gs_update_kernel<16>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
+          else launch_pdl(ctx, "gs_update", gs_update_kernel<24>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
+        }
+        const int np1 = pn + 1;
+        if ((np1 & (np1 - 1)) == 0 || np1 >= nominal) {   // 1, 2, 4, 8, ... panels, then every panel: has the factorisation finished?
+          QTT_CUDA(cudaMemcpyAsync(h_done, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+          QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+          if (*h_done) return true;
+        }
+      }
+      return false;
+    };
+    // Rank-deficient tensors under `mindim` (the first sweeps of the benchmark: rank 2 ... 200, mindim 256): the Householder
+    // variant gets the orthonormal completion for free from its accumulated Q, so it is the better choice while the rank is
+    // small; the last split's rank (ranks vary smoothly along a chain) decides which variant goes first.
+    const bool hh_first = ctx->qr_last_need == need && ctx->qr_last_rank >= 0 && ctx->qr_last_rank < (int)(0.45 * need);
+    if (!hh_first) gs_done = run_panels(Zw, q, norms, rowstate, kmax, 0, true, 0.0);
+    if (gs_dbg) {
+      long long h[16];
+      cudaMemcpy(h, gs_dbg, 128, cudaMemcpyDeviceToHost);
+      if (h[8] > 0)
+        fprintf(stderr, "[qtt trace]   gs_panel cycles per panel: load %.0f norms %.0f gram %.0f cholesky+inverse %.0f apply %.0f gram2 %.0f apply2 %.0f store %.0f (%lld panels)\n",
+                (double)h[0] / h[8], (double)h[1] / h[8], (double)h[2] / h[8], (double)h[3] / h[8], (double)h[4] / h[8], (double)h[5] / h[8],
+                (double)h[6] / h[8], (double)h[7] / h[8], h[8]);
+    }
+    if (gs_done) {
+      launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 0);
+      int* h_r = reinterpret_cast<int*>(ctx->h_scal + 16);
+      QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+      const int r_num = *h_r;
+      ctx->qr_last_rank = r_num;
+      ctx->qr_last_need = need;
+      if (r_num < need) {
+        if (r_num < (int)(0.45 * need)) {
+          gs_done = false;   // far below `mindim`: Householder path (its accumulated Q is the orthonormal completion)
+        } else {
+          // completion: Gram-Schmidt continues on the rows of the projector I - Q^T Q until `need` basis rows exist;
+          // their R part stays zero (sigma = 0: never rotated, sorted last, kept only because of `mindim`)
+          double* Zw2 = SE + (size_t)q * ldp;
+          double* norms2 = ctx->arena.alloc(p);
+          int* rowstate2 = reinterpret_cast<int*>(ctx->arena.alloc(p / 2 + 1));
+          GemmDesc gp;   // Zw2 (p x p) = -Q^T Q
+          gp.A = Y + qd; gp.B = Y + qd; gp.C = Zw2; gp.transA = true;
+          gp.M = p; gp.N = p; gp.K = r_num; gp.lda = ldy; gp.ldb = ldy; gp.ldc = ldp; gp.alpha = -1.0; gp.beta = 0.0;
+          gemm(ctx, gp);
+          int grid = (p + 7) / 8;
+          if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
+          launch_pdl(ctx, "gs_projector", gs_projector_kernel, dim3(grid), dim3(256), 0, Zw2, p, ldp, norms2, rowstate2);
+          launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 1);
+          const bool ok = run_panels(Zw2, p, norms2, rowstate2, need, r_num, false, 1e-12);
+          launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 0);
+          QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+          QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+          if (!ok || *h_r < need) gs_done = false;
+        }
+      }
+    }
+  }
+  if (!gs_done) {
     int rows = q + p;
     int grid = (rows + 7) / 8;
     if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
@@ -1476,7 +2036,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     set_smem(qr_apply_kernel<16>, 200 * 1024);
     set_smem(qr_apply_kernel<32>, 200 * 1024);
   }
-  const int npanels = (kmax + nb - 1) / nb;
+  const int npanels = gs_done ? 0 : (kmax + nb - 1) / nb;
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;
   if (agrid > ctx->sms) agrid = ctx->sms;
   for (int pn = 0; pn < npanels; ++pn) {
@@ -1489,14 +2049,13 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     else if (p <= 1024) launch_pdl(ctx, "qr_apply", qr_apply_kernel<32>, dim3(agrid), dim3(PANEL_T), smem_apply, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
     else launch_pdl(ctx, "qr_apply", qr_apply_generic_kernel, dim3(agrid), dim3(PANEL_T), 0, SE, q, p, ldp, rowstate, inpanel, Vp, taus, norms, ctl);
   }
-  const bool trace = ctx->profiling && getenv("QTT_TRACE") != nullptr;
   cudaEvent_t evq = nullptr, evj = nullptr;
   if (trace) {
     cudaEventCreate(&evq);
     cudaEventCreate(&evj);
     cudaEventRecord(evq, ctx->stream);
   }
-  {
+  if (!gs_done) {
     dim3 grid((q + p + 31) / 32, (kmax + 31) / 32);
     launch_pdl(ctx, "build_y", build_y_kernel, grid, dim3(32, 8), 0, SE, q, p, ldp, qd, ldy, Y, ctl);
   }
@@ -1529,8 +2088,10 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     // the grid and the block size follow the numerical rank: one 4-byte read-back (the split synchronises for the kept rank anyway)
     int* h_r = reinterpret_cast<int*>(ctx->h_scal + 16);
     QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QTT_CUDA(cudaMemcpyAsync(h_r + 1, &ctl->rj, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*h_r >= 32) launched = launch_jq_gram(ctx, a, *h_r);
+    const int r_rot = h_r[1] > 0 ? h_r[1] : h_r[0];
+    if (r_rot >= 32) launched = launch_jq_gram(ctx, a, r_rot);
   }
   if (launched) {
   } else if (half <= 1024 && kmax >= 16) {
@@ -1563,7 +2124,11 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     cudaEventSynchronize(evj);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evq, evj);
-    fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: numerical rank %d, jacobi %d sweeps %.3f ms (after QR)\n", q, p, h_info[3], h_info[1], ms);
+    float msq = 0.f;
+    cudaEventElapsedTime(&msq, evq0, evq);
+    cudaEventDestroy(evq0);
+    fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: %s QR %.3f ms, numerical rank %d, jacobi %d sweeps %.3f ms\n", q, p,
+            gs_done ? "Gram-Schmidt" : "Householder", msq, h_info[3], h_info[1], ms);
     if (a.dbg) {
       long long h[32];
       cudaMemcpy(h, a.dbg, 256, cudaMemcpyDeviceToHost);
@@ -1590,6 +2155,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   res.sweeps = h_info[1];
   res.truncerr = *h_err;
   if (!h_info[2]) fail(QTT_ERR_NOCONV, "Jacobi SVD did not converge in %d sweeps (q=%d, p=%d, rank %d)", max_sweeps, q, p, h_info[3]);
+  if (!gs_done) { ctx->qr_last_rank = h_info[3]; ctx->qr_last_need = need; }
+  if (gs_done && res.k > h_info[3]) fail(QTT_ERR_UNSUPPORTED, "svd_rows_qr: %d rows kept but only %d basis rows exist on the Gram-Schmidt path", res.k, h_info[3]);
   res.Wn = ctx->arena.alloc((size_t)res.k * p);
   res.Wni = nullptr;
   dim3 grid2((p + 255) / 256, res.k);

@@ -429,14 +429,24 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   DBuf dump_store;
   if (trace && getenv("QTT_DUMP") && sscanf(getenv("QTT_DUMP"), "%d,%d,%d,%500s", &dump_sw, &dump_dir, &dump_bond, dump_path_buf) == 4)
     dump_path = dump_path_buf;
-  if (!P.x0_canonical) right_orthonormalize(ctx, x);
-
+  // The per-call set-up (orthogonalize!, right-environment build) is part of the FIRST sweep's device time: the events
+  // bracket everything a `linsolve(...; nsweeps)` call enqueues.
+  cudaEvent_t evs0 = nullptr, evs1 = nullptr;
+  QTT_CUDA(cudaEventCreate(&evs0));
+  QTT_CUDA(cudaEventCreate(&evs1));
   std::vector<DBuf> LA(n + 1), RA(n + 1), LB(n + 1), RB(n + 1);
   auto cleanup = [&]() {
     for (auto* v : {&LA, &RA, &LB, &RB})
       for (auto& d : *v) dbuf_free(d);
+    if (evs0) cudaEventDestroy(evs0);
+    if (evs1) cudaEventDestroy(evs1);
+    evs0 = evs1 = nullptr;
   };
   try {
+    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+    auto t_call = std::chrono::steady_clock::now();
+    QTT_CUDA(cudaEventRecord(evs0, ctx->stream));
+    if (!P.x0_canonical) right_orthonormalize(ctx, x);
     set_one(ctx, LA[0]);
     set_one(ctx, RA[n]);
     if (b) { set_one(ctx, LB[0]); set_one(ctx, RB[n]); }
@@ -474,13 +484,13 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
 
     for (int j = n - 1; j >= 2; --j) update_right(j);
 
-    cudaEvent_t evs0 = nullptr, evs1 = nullptr;
-    QTT_CUDA(cudaEventCreate(&evs0));
-    QTT_CUDA(cudaEventCreate(&evs1));
     for (int sw = 0; sw < P.nsweeps; ++sw) {
-      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-      auto t0 = std::chrono::steady_clock::now();
-      QTT_CUDA(cudaEventRecord(evs0, ctx->stream));
+      auto t0 = t_call;
+      if (sw > 0) {
+        QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+        t0 = std::chrono::steady_clock::now();
+        QTT_CUDA(cudaEventRecord(evs0, ctx->stream));
+      }
       qtt_sweep_info info;
       memset(&info, 0, sizeof(info));
       const int maxdim = P.maxdim ? P.maxdim[sw] : 0;
@@ -664,8 +674,6 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
       }
       if (infos) infos[sw] = info;
     }
-    cudaEventDestroy(evs0);
-    cudaEventDestroy(evs1);
   } catch (...) {
     cleanup();
     dbuf_free(dump_store);

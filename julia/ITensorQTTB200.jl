@@ -107,16 +107,30 @@ function mps_cores(x::MPS)
   return cores, chi
 end
 
-# MPO core j as array(A[j], l, r, s, s')  (index order of reference src/laplacian.jl:32)
+# The input (plev 0) and output (plev 1) site index of MPO tensor j, whatever their ids: `dft_mpo` relabels the outputs
+# (`reverse_output_bits`, reference src/dft.jl:76-79,98), so tensor j of a DFT MPO carries (s_j, s_{n+1-j}'), and
+# `idft_mpo = swapprime(dag(dft_mpo))` carries (s_{n+1-j}, s_j').
+function mpo_site_inds(A::MPO, j::Int)
+  links = Index[]
+  j > 1 && push!(links, linkind(A, j - 1))
+  j < length(A) && push!(links, linkind(A, j))
+  sites = [i for i in inds(A[j]) if !(i in links)]
+  length(sites) == 2 || error("MPO tensor $j: expected two site indices, found $(length(sites))")
+  sin = only(filter(i -> plev(i) == 0, sites))
+  sout = only(filter(i -> plev(i) == 1, sites))
+  return sin, sout
+end
+
+# MPO core j as array(A[j], l, r, s_in, s_out)  (index order of reference src/laplacian.jl:32)
 function mpo_cores(A::MPO)
   n = length(A)
   cores = Vector{Array}(undef, n)
   w = ones(Int64, n + 1)
   for j in 1:n
-    s = siteind(A, j; plev=0)
+    s, sp = mpo_site_inds(A, j)
     l = j > 1 ? linkind(A, j - 1) : nothing
     r = j < n ? linkind(A, j) : nothing
-    is = filter(!isnothing, (l, r, s, s'))
+    is = filter(!isnothing, (l, r, s, sp))
     a = array(A[j], is...)
     dl = isnothing(l) ? 1 : dim(l)
     dr = isnothing(r) ? 1 : dim(r)
@@ -252,14 +266,19 @@ function dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim=typem
   end
 end
 
-# `apply(A, psi; cutoff, maxdim, mindim)` (density-matrix algorithm); output on `noprime` of A's primed site indices
+# `apply(A, psi; cutoff, maxdim, mindim)` (density-matrix algorithm); like ITensors `apply`, the output MPS carries
+# `noprime` of A's OUTPUT site indices (for a DFT MPO: s_{n+1-j} on tensor j)
 function apply_mpo(A::MPO, psi::MPS; cutoff=1e-13, maxdim=0, mindim=1, ctx::Context=context())
+  for j in 1:length(A)
+    mpo_site_inds(A, j)[1] == siteind(psi, j) || error("apply_mpo: input site index of MPO tensor $j is not the site index of MPS tensor $j")
+  end
+  sout = [noprime(mpo_site_inds(A, j)[2]) for j in 1:length(A)]
   hA = upload(ctx, A); hp = upload(ctx, psi)
   out = Ref{Ptr{Cvoid}}(C_NULL)
   try
     check(ctx, ccall((:qtt_apply, libqtt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int32, Int32, Ptr{Ptr{Cvoid}}),
                      ctx.handle, hA, hp, cutoff, maxdim, mindim, out))
-    return download(ctx, out[], siteinds(psi))
+    return download(ctx, out[], sout)
   finally
     out[] != C_NULL && free_mps(out[]); free_mps(hp); free_mpo(hA)
   end
@@ -273,23 +292,36 @@ function cached_dft_mpo(s; cutoff, inverse=false)
   F = get!(_dft_cache, key) do
     inverse ? idft_mpo(s; cutoff) : dft_mpo(s; cutoff)
   end
-  s0 = [siteind(F, j; plev=0) for j in 1:length(F)]
+  # the site indices the cached MPO was built on, in chain order: dft_mpo has s_j unprimed on tensor j, idft_mpo has s_j primed
+  s0 = inverse ? [noprime(mpo_site_inds(F, j)[2]) for j in 1:length(F)] : [mpo_site_inds(F, j)[1] for j in 1:length(F)]
   return s0 == s ? F : replace_siteinds(F, s0, s)
 end
-replace_siteinds(F::MPO, old, new) = MPO([replaceinds(F[j], (old[j], old[j]') => (new[j], new[j]')) for j in 1:length(F)])
+# every site index of every tensor is mapped by id and keeps its prime level (tensor j does NOT carry (s_j, s_j'))
+function replace_siteinds(F::MPO, old, new)
+  function relabel(T)
+    for i in inds(T)
+      k = findfirst(==(noprime(i)), old)
+      isnothing(k) || (T = replaceind(T, i, setprime(new[k], plev(i))))
+    end
+    return T
+  end
+  return MPO([relabel(F[j]) for j in 1:length(F)])
+end
 
-function apply_dft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
+# reference src/dft.jl:121-126: reverse(apply(dft_mpo(s), psi; kwargs...)) -- the OUTPUT chain is reversed
+function apply_dft_mpo(psi::MPS; kwargs...)
   s = siteinds(psi)
-  F = cached_dft_mpo(s; cutoff)
-  phi = apply_mpo(F, psi; cutoff, kwargs...)
+  F = cached_dft_mpo(s; cutoff=1e-15)
+  phi = apply_mpo(F, psi; kwargs...)
   return MPS(reverse([phi[j] for j in 1:length(phi)]))
 end
 
-function apply_idft_mpo(psi::MPS; cutoff=1e-15, kwargs...)
+# reference src/dft.jl:128-133: apply(idft_mpo(s), reverse(psi); kwargs...) -- the INPUT chain is reversed, the result is not
+function apply_idft_mpo(psi::MPS; kwargs...)
   s = siteinds(psi)
-  F = cached_dft_mpo(s; cutoff, inverse=true)
-  phi = apply_mpo(F, psi; cutoff, kwargs...)
-  return MPS(reverse([phi[j] for j in 1:length(phi)]))
+  F = cached_dft_mpo(s; cutoff=1e-15, inverse=true)
+  rpsi = MPS(reverse([psi[j] for j in 1:length(psi)]))
+  return apply_mpo(F, rpsi; kwargs...)
 end
 
 # `+(x, y; cutoff, maxdim)` of ITensorMPS (reference src/fourier_interpolation.jl:8, src/function_to_mps.jl:123) on the device:
