@@ -1415,7 +1415,7 @@ bool launch_jq_gram(Ctx* ctx, JqArgs& a, int r) {
 // falls back to the Householder variant, whose accumulated Q supplies the orthonormal completion.
 constexpr int GSB = 32;           // panel height
 constexpr int GST = 512;          // threads of the panel kernel
-constexpr double GS_DEFER = 1e-6; // pivot threshold relative to the row's own squared norm
+constexpr double GS_DEFER = 1e-3; // pivot threshold relative to the row's own squared norm: an accepted row keeps >= 3% of its norm, so normalising it amplifies the rounding of its re-orthogonalisation (eps) by <= 30 (at 1e-6: isometry of the factors 3e-13, measured)
 
 __global__ void gs_init_kernel(const double* __restrict__ M, int q, int p, int ldp, double* __restrict__ Zw, double* __restrict__ norms,
                                int* __restrict__ rowstate, QrCtl* ctl) {
@@ -2011,7 +2011,9 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
           if (grid > 4 * ctx->sms) grid = 4 * ctx->sms;
           launch_pdl(ctx, "gs_projector", gs_projector_kernel, dim3(grid), dim3(256), 0, Zw2, p, ldp, norms2, rowstate2);
           launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 1);
-          const bool ok = run_panels(Zw2, p, norms2, rowstate2, need, r_num, false, 1e-12);
+          // rows of the projector with squared norm above 0.05 only (their sum is p - r >= need - r, so there are always enough):
+          // normalising a short row would amplify the rounding of its orthogonalisation (measured: isometry 1e-11 at 1e-12)
+          const bool ok = run_panels(Zw2, p, norms2, rowstate2, need, r_num, false, 0.05);
           launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 0);
           QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
           QTT_CUDA(cudaStreamSynchronize(ctx->stream));
