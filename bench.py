@@ -292,6 +292,83 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_cfg5(args):
+    """BASELINE configs[4]: batched Helmholtz wavenumber sweep, independent n = 28, chi = 128 solves sharded over the ranks
+    (instance i -> rank i mod N, no data-path collective; NCCL gathers the residuals).  A step = this rank's `--instances`
+    solves (2 fixed-work sweeps each), spread over `--streams` host threads with one context (= one CUDA stream) each: at
+    chi = 128 every kernel is launch-latency bound, so concurrent instances overlap on the GPU.  `value` = instances/s over all
+    ranks, timed on the host clock around device-synchronised steps (the instances run on several streams at once; there is
+    no single stream to put CUDA events on)."""
+    import torch
+    import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
+    import itensorqtt_jl_b200 as q
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (libqtt_b200 has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, chi, T, ninst = 28, 128, max(1, args.streams), args.instances
+    A = q.laplacian_mpo(n, 1.0)
+    b = q.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
+    ctxs = [q.Context(local) for _ in range(T)]
+    dev = [(q.DeviceMPO(A, c), q.DeviceMPS(b, c)) for c in ctxs]
+    x0 = q.random_mps(n, chi, 2)
+
+    def solve(i, t):
+        k = 2 * np.pi * (2 ** 16 + i * world + rank)       # global instance id i * world + rank
+        lam = -((k / 2 ** n) ** 2)
+        x, info = q.linsolve(dev[t][0], dev[t][1], x0, -lam, 1.0, nsweeps=2, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
+                             x0_canonical=True, ctx=ctxs[t], return_info=True, on_device=True)
+        x.free()
+        return info[-1]["solver_resid"]
+
+    def step():
+        with ThreadPoolExecutor(T) as ex:
+            return [r for part in ex.map(lambda t: [solve(i, t) for i in range(t, ninst, T)], range(T)) for r in part]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = sum(c.launches for c in ctxs)
+    t0 = time.perf_counter()
+    res = []
+    for _ in range(args.steps):
+        res = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(c.launches for c in ctxs) - l0
+    t = torch.tensor([dt, max(res) if res else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        allt = torch.stack(parts).cpu().numpy()
+    else:
+        allt = t.cpu().numpy()[None]
+    if rank == 0:
+        tmax = float(allt[:, 0].max())
+        out = {"metric": "batched Helmholtz wavenumber sweep, instances/s (n=28, chi=128)", "value": world * ninst * args.steps / tmax,
+               "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmax / args.steps * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "cfg5: independent Helmholtz solves n=28 chi=128 (2 fixed-work sweeps each, %d Arnoldi steps per bond), "
+                                      "%d instances per rank and step on %d streams" % (args.krylov, ninst, T),
+                          "instances_per_step": world * ninst, "l2": "working set per instance 60 MB x %d concurrent instances > L2" % T,
+                          "timing": "host clock around device-synchronised steps, max over ranks"},
+               "clocks": clocks, "gpu_launches": int(launches), "residual_max": float(allt[:, 1].max())}
+        print(json.dumps(out))
+        sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_sweeps(args, max_sweeps, budget_s):
     """The oracle port (numpy tensordot -> OpenBLAS dgemm, LAPACK gesdd, KrylovKit-style GMRES) timed on the host cores on
     WHOLE two-site sweeps of the same workload (58 bond updates each at n = 30), chained from the random start like the GPU
@@ -363,10 +440,15 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU sweeps the reference arm may time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list runs)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = BASELINE headline (default); cfg5 = batched n=28 chi=128 instances")
+    ap.add_argument("--instances", type=int, default=8, help="cfg5: instances per rank and step")
+    ap.add_argument("--streams", type=int, default=8, help="cfg5: concurrent contexts (CUDA streams) per rank")
     ap.add_argument("--roofline-reps", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 

@@ -79,6 +79,9 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
     infos = (SweepInfo * max(p.nsweeps, 1))()
     try:
         check(ctx.handle, lib.qtt_linsolve(ctx.handle, dA.handle, db.handle, dx.handle, C.byref(p), infos))
+    except Exception:
+        dx.free()      # the working copy of x0 must not outlive a failed solve
+        raise
     finally:
         if fa:
             dA.free()
@@ -121,6 +124,9 @@ def dmrg_target(A, psi0, *, target_eigenvalue, nsweeps=None, maxdim=None, mindim
     infos = (SweepInfo * max(p.nsweeps, 1))()
     try:
         check(ctx.handle, lib.qtt_dmrg_target(ctx.handle, dA.handle, dx.handle, C.byref(p), infos))
+    except Exception:
+        dx.free()
+        raise
     finally:
         if fa:
             dA.free()

@@ -337,6 +337,7 @@ void apply_mpo_mps(Ctx* ctx, const Mpo& A, const Mps& psi, double cutoff, int ma
   auto free_env = [&]() {
     for (auto& e : E) dbuf_free(e.buf);
   };
+  Persist carry;  // Rk (a, p, k): the running right factor of the density-matrix pass
   try {
     {
       Persist e0;
@@ -359,7 +360,7 @@ void apply_mpo_mps(Ctx* ctx, const Mpo& A, const Mps& psi, double cutoff, int ma
       dbuf_free(e0.buf);
     }
     // right-to-left: rho -> eigen -> carry
-    Persist carry;  // Rk (a, p, k)
+    // (carry is declared before the try block so that the error path can release it)
     int k = 1;
     {
       size_t mk = ctx->arena.mark();
@@ -410,6 +411,7 @@ void apply_mpo_mps(Ctx* ctx, const Mpo& A, const Mps& psi, double cutoff, int ma
     }
     dbuf_free(carry.buf);
   } catch (...) {
+    dbuf_free(carry.buf);
     free_env();
     throw;
   }

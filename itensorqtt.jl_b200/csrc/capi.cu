@@ -2,6 +2,7 @@
 // caught here and turned into a status code + message.
 #include "common.cuh"
 #include <mutex>
+#include <set>
 #include <map>
 #include <unordered_map>
 
@@ -20,6 +21,7 @@ namespace {
 struct PoolBlock { void* p; size_t bytes; cudaStream_t st; };
 struct DevicePool { std::multimap<size_t, PoolBlock> free_blocks; std::unordered_map<void*, size_t> live; size_t cached = 0; };
 std::mutex g_pool_mutex;
+std::set<cudaStream_t> g_live_streams;  // streams of live contexts (guarded by g_pool_mutex)
 std::map<int, DevicePool> g_pools;
 thread_local Ctx* tl_ctx = nullptr;
 
@@ -80,6 +82,8 @@ void pool_free(void* p, cudaStream_t st) {
   }
   const size_t bytes = it->second;
   P.live.erase(it);
+  // a chain may outlive the context that allocated it: a block tagged with a destroyed stream must never be synchronised on
+  if (st != nullptr && g_live_streams.count(st) == 0) st = nullptr;
   P.free_blocks.emplace(bytes, PoolBlock{p, bytes, st});
   P.cached += bytes;
 }
@@ -98,6 +102,7 @@ void pool_trim() {
 // a stream is about to be destroyed: its cached blocks become quiescent
 static void pool_forget_stream(cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_pool_mutex);
+  g_live_streams.erase(st);
   for (auto& dp : g_pools)
     for (auto& kv : dp.second.free_blocks)
       if (kv.second.st == st) kv.second.st = nullptr;
@@ -219,6 +224,10 @@ qtt_ctx* qtt_ctx_create(int device) {
     c->cc_minor = prop.minor;
     c->clock_khz = prop.clockRate;
     QTT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mutex);
+      g_live_streams.insert(c->stream);
+    }
     QTT_CUDA(cudaMalloc(&c->d_scal, 16384 * sizeof(double)));
     QTT_CUDA(cudaMemset(c->d_scal, 0, 16384 * sizeof(double)));
     QTT_CUDA(cudaMalloc(&c->d_sync, 256 * sizeof(unsigned)));

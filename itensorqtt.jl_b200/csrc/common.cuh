@@ -10,6 +10,7 @@
 #include <string>
 #include <stdexcept>
 #include <cstdlib>
+#include <mutex>
 #include "../../include/qtt_b200.h"
 
 namespace qtt {
@@ -81,7 +82,7 @@ struct Ctx {
   int qr_last_rank = -1, qr_last_need = 0;  // numerical rank / mindim of the last split: picks the QR variant that goes first (svd_qr.cu)
   bool profiling = false;
   // small device scratch for scalars / flags / partial reductions
-  double* d_scal = nullptr;      // 4096 doubles
+  double* d_scal = nullptr;      // 16384 doubles (GMRES scalar blocks at 0 and 8192, statistics at 8 ...)
   double* d_partial = nullptr;   // partial reduction buffer
   size_t partial_cap = 0;
   unsigned int* d_sync = nullptr;  // grid-barrier counters and flags (256 uints)
@@ -93,14 +94,19 @@ struct Ctx {
 };
 
 // cudaFuncSetAttribute is a per-DEVICE setting: a call site configures its kernel once per device, not once per process
-// (one process may drive several GPUs through several contexts).
+// (one process may drive several GPUs through several contexts).  Thread-safe: batch.py drives one context per host thread
+// and ctypes releases the GIL, so two threads can reach the same first use; the flag is set only AFTER the set-up has run,
+// under the lock, and a thread that loses the race waits for it.
 struct DevOnce {
+  std::mutex mu;
   bool done[64] = {};
-  bool first(int dev) {
-    if (dev < 0 || dev >= 64) return true;
-    if (done[dev]) return false;
+  template <typename F>
+  void run(int dev, F&& setup) {
+    if (dev < 0 || dev >= 64) { setup(); return; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return;
+    setup();
     done[dev] = true;
-    return true;
   }
 };
 

@@ -389,9 +389,9 @@ void dense_qr_rows(Ctx* ctx, double* base, const DenseLayout& d, int n, int nrow
       pa.part = base + d.part; pa.bar = ctx->d_sync + 240; pa.epoch = ctx->dense_epoch; pa.slice = slice;
       const size_t smem = sizeof(double) * (size_t)DNB * slice;
       static DevOnce once;
-      if (once.first(ctx->device)) {
+      once.run(ctx->device, [&] {
         QTT_CUDA(cudaFuncSetAttribute(dqr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      }
+      });
       void* args[] = {&pa};
       QTT_CUDA(cudaLaunchCooperativeKernel((void*)dqr_panel_kernel, dim3(G), dim3(PANEL_THREADS), args, smem, ctx->stream));
       ctx->launches++;
@@ -417,7 +417,7 @@ void dense_qr_rows(Ctx* ctx, double* base, const DenseLayout& d, int n, int nrow
 void launch_tri(Ctx* ctx, TriArgs& a) {
   const size_t smem = sizeof(double) * (size_t)a.n * (a.eigen ? 2 : 1);
   static DevOnce once;  // (the kernel's 8.7 KB of static shared memory count against the 48 KB default)
-  if (once.first(ctx->device)) QTT_CUDA(cudaFuncSetAttribute(dtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  once.run(ctx->device, [&] { QTT_CUDA(cudaFuncSetAttribute(dtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); });
   dtri_kernel<<<1, DPT, smem, ctx->stream>>>(a);
   check_launch(ctx, "dtri");
 }

@@ -217,9 +217,9 @@ void launch_cfg(Ctx* ctx, const GemmArgs& a, int batch_total) {
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, STAGES, TA, TB, VEC>;
   constexpr size_t smem = smem_bytes<BM, BN, STAGES, TA, TB>();
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  });
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, batch_total);
   launch_pdl(ctx, "gemm_dmma", kern, grid, dim3(WM * WN * 32), smem, a);
 }

@@ -582,7 +582,7 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   }
   const size_t smem = (base + (size_t)kstash * per) * sizeof(double);
   static DevOnce once;
-  if (once.first(ctx->device)) QTT_CUDA(cudaFuncSetAttribute(cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+  once.run(ctx->device, [&] { QTT_CUDA(cudaFuncSetAttribute(cgs2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET)); });
   Cgs2Args a;
   a.V = V; a.k = k; a.len = len; a.w = w; a.vnext = vnext; a.S = S;
   a.part = ctx->partial((size_t)3 * G * 64);

@@ -303,9 +303,9 @@ bool gmres_small_ok(int chil, int chir, int wl, int wr, int kd) {
 void gmres_small(Ctx* ctx, const double* L, const double* W12, const double* R, const double* beff, double* x, int chil, int chir, int wl,
                  int wr, double a0, double a1, double tol, int kd, int maxiter, bool fixed, double* V, double* stats_dev) {
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(gmres_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_BUDGET));
-  }
+  });
   SmallArgs a;
   a.L = L; a.W12 = W12; a.R = R; a.beff = beff; a.x = x; a.V = V;
   a.chil = chil; a.chir = chir; a.wl = wl; a.wr = wr;

@@ -433,9 +433,9 @@ void launch_mva(Ctx* ctx, const MvAArgs& a) {
   auto kern = matvec_a_kernel<WL, MI, WM, WN, VEC>;
   constexpr size_t smem = mva_smem<WL, MI, WM, WN>();
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  });
   dim3 grid((a.chil + 8 * MI * WM - 1) / (8 * MI * WM), (a.chir + 8 * WN - 1) / (8 * WN));
   launch_pdl(ctx, "matvec_a", kern, grid, dim3(WM * WN * 32), smem, a);
 }
@@ -505,12 +505,12 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
   constexpr size_t smemB32 = (size_t)6 * (32 * (BK + 4) + BK * (32 + 4)) * sizeof(double);
   constexpr size_t smemB_max = smemB64 > 116 * 1024 ? smemB64 : 116 * 1024;
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
     QTT_CUDA(cudaFuncSetAttribute(matvec_b_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
-  }
+  });
   {
     const long ctas64 = (long)((b.M + 31) / 32) * ((b.N + 63) / 64);
     static const int bn_env = getenv("QTT_MVB_BN") ? atoi(getenv("QTT_MVB_BN")) : 0;

@@ -258,10 +258,10 @@ void mps_sample(Ctx* ctx, const Mps& x, const int64_t* idx_dev, int64_t count, d
   const size_t smem = (size_t)2 * (cplx ? 2 : 1) * a.chimax * sizeof(double);
   QTT_REQUIRE(smem <= 200 * 1024, "mps_sample: bond dimension %d exceeds the shared-memory row-vector budget", a.chimax);
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     QTT_CUDA(cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
+  });
   const unsigned grid = (unsigned)std::min<int64_t>(count, (int64_t)ctx->sms * 8);
   if (cplx) sample_kernel<true><<<grid, 256, smem, ctx->stream>>>(a);
   else sample_kernel<false><<<grid, 256, smem, ctx->stream>>>(a);

@@ -769,9 +769,9 @@ __global__ void __launch_bounds__(64 * JBT) jacobi_qr_block_kernel(JqArgs a) {
 template <int NC, int JBT>
 void launch_jq_block(Ctx* ctx, JqArgs& a, int grid, size_t smem) {
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(jacobi_qr_block_kernel<NC, JBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
+  });
   void* args[] = {&a};
   QTT_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_qr_block_kernel<NC, JBT>, dim3(grid), dim3(64 * JBT), args, smem, ctx->stream));
   ctx->launches++;
@@ -1339,7 +1339,7 @@ bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int r) {
   static int maxcl[64][2] = {};
   const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
   const int css[2] = {8, 5};
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     QTT_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     for (int k = 0; k < 2; ++k) {
       cudaLaunchConfig_t cfg = {};
@@ -1355,7 +1355,7 @@ bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int r) {
       (void)cudaGetLastError();
       maxcl[dv][k] = n;
     }
-  }
+  });
   static const int cs_env = getenv("QTT_JACOBI_CS") ? atoi(getenv("QTT_JACOBI_CS")) : 0;
   int ki = 0;
   if (K::UTE % 5 == 0 && (K::UTE / 5) % 2 == 0 && (cs_env == 5 || (cs_env == 0 && nslots > maxcl[dv][0] && nslots <= maxcl[dv][1]))) ki = 1;
@@ -1914,12 +1914,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   bool gs_done = false;
   if (!gs_off && p % 2 == 0 && kmax >= 64 && gs_smem <= 220 * 1024) {
     static DevOnce gs_once;
-    if (gs_once.first(ctx->device)) {
+    gs_once.run(ctx->device, [&] {
       set_smem(gs_panel_kernel, 220 * 1024);
       set_smem(gs_update_kernel<8>, 200 * 1024);
       set_smem(gs_update_kernel<16>, 200 * 1024);
       set_smem(gs_update_kernel<24>, 200 * 1024);
-    }
+    });
     double* Zw = SE;   // the (q + p) x ldp Householder workspace is free on this path
     double* Pbuf = ctx->arena.alloc((size_t)GSB * ldp);
     double* C2 = ctx->arena.alloc((size_t)(kmax + GSB) * GSB);
@@ -2032,12 +2032,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   const size_t smem_panel = ((size_t)nb * ldp + q) * sizeof(double);
   const size_t smem_apply = (size_t)nb * ldp * sizeof(double);
   static DevOnce once;
-  if (once.first(ctx->device)) {
+  once.run(ctx->device, [&] {
     set_smem(qr_panel_kernel, 200 * 1024);
     set_smem(qr_apply_kernel<8>, 200 * 1024);
     set_smem(qr_apply_kernel<16>, 200 * 1024);
     set_smem(qr_apply_kernel<32>, 200 * 1024);
-  }
+  });
   const int npanels = gs_done ? 0 : (kmax + nb - 1) / nb;
   int agrid = (q + p + PANEL_W - 1) / PANEL_W;
   if (agrid > ctx->sms) agrid = ctx->sms;

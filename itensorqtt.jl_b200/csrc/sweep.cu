@@ -239,9 +239,9 @@ void lanczos_local(Ctx* ctx, const MatvecFn& mv, double* x, size_t len, double t
   auto run_ritz = [&]() {
     constexpr int kRitzSmem = 2 * 64 * 65 * (int)sizeof(double);
     static DevOnce once;
-    if (once.first(ctx->device)) {
+    once.run(ctx->device, [&] {
       QTT_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRitzSmem));
-    }
+    });
     ritz_kernel<<<1, 32, kRitzSmem, ctx->stream>>>(S, kd, 64, target, which, S + OFF_YK);
     check_launch(ctx, "ritz");
   };

@@ -62,6 +62,101 @@ def retraction_mpo(n_fine):
     return [np.transpose(c, (0, 1, 3, 2)).copy() for c in prolongation_mpo(n_fine)]
 
 
+# ---- N-D grids: dimensions interleaved site by site (reference src/mps_utils.jl:55-66 `interleave`) -----------------------
+def _identity_mpo(n):
+    return [np.eye(2).reshape(1, 1, 2, 2) for _ in range(n)]
+
+
+def interleave_mpo(*chains):
+    """`interleave(M_1, ..., M_D)`: site j of chain d lands on site j*D + d; while the other chains' sites pass, a chain's
+    open link rides along as an identity factor of the combined link (Kronecker structure)."""
+    D, n = len(chains), len(chains[0])
+    assert all(len(c) == n for c in chains)
+    links = [1] * D                     # open link of every chain to the left of the current site
+    out = []
+    for j in range(n):
+        for d in range(D):
+            core = chains[d][j]
+            wl, wr = core.shape[:2]
+            assert wl == links[d]
+            left = int(np.prod(links))
+            before = int(np.prod(links[:d])); after = int(np.prod(links[d + 1:]))
+            T = np.einsum("ab,lrst,cd->alcbrdst", np.eye(before), core, np.eye(after))
+            links[d] = wr
+            out.append(T.reshape(left, int(np.prod(links)), 2, 2))
+    return out
+
+
+def interleave_mps(*chains):
+    """`interleave(psi_1, ..., psi_D)` for states (same rule as interleave_mpo)."""
+    D, n = len(chains), len(chains[0])
+    links = [1] * D
+    out = []
+    for j in range(n):
+        for d in range(D):
+            core = chains[d][j]
+            al, _, ar = core.shape
+            assert al == links[d]
+            left = int(np.prod(links))
+            before = int(np.prod(links[:d])); after = int(np.prod(links[d + 1:]))
+            T = np.einsum("ab,lsr,cd->alcsbrd", np.eye(before), core, np.eye(after))
+            links[d] = ar
+            out.append(T.reshape(left, 2, int(np.prod(links))))
+    return out
+
+
+def mpo_directsum(A, B):
+    """`+(A, B; alg="directsum")` for two MPOs of equal length: block-diagonal links, shared boundary links of dimension 1."""
+    n = len(A)
+    assert len(B) == n
+    out = []
+    for j, (a, b) in enumerate(zip(A, B)):
+        al, ar = a.shape[:2]; bl, br = b.shape[:2]
+        L = 1 if j == 0 else al + bl
+        R = 1 if j == n - 1 else ar + br
+        T = np.zeros((L, R, 2, 2), dtype=np.result_type(a, b))
+        if j == 0:
+            T[0:1, 0:ar] = a; T[0:1, ar:ar + br] = b
+        elif j == n - 1:
+            T[0:al, 0:1] = a; T[al:al + bl, 0:1] = b
+        else:
+            T[0:al, 0:ar] = a; T[al:, ar:] = b
+        out.append(T)
+    return out
+
+
+def laplacian_mpo_nd(nbits, xstep=None):
+    """`laplacian_mpo(s::Tuple{...}, xstep::Tuple)` (reference src/laplacian.jl:45-53), any number of equal-length
+    dimensions: sum over d of interleave(I, ..., Delta_d, ..., I), added by direct sum."""
+    D = len(nbits)
+    assert len(set(nbits)) == 1, "interleaved dimensions need equal bit counts"
+    xstep = xstep or (1.0,) * D
+    total = None
+    for d in range(D):
+        parts = [laplacian_mpo(nbits[k], xstep[k]) if k == d else _identity_mpo(nbits[k]) for k in range(D)]
+        term = interleave_mpo(*parts)
+        total = term if total is None else mpo_directsum(total, term)
+    return total
+
+
+def prolongation_mpo_nd(nbits_fine):
+    """`prolongation_mpo(s::Tuple)` (reference src/prolongation.jl:25-27): interleave of the 1-D prolongation MPOs."""
+    return interleave_mpo(*[prolongation_mpo(n) for n in nbits_fine])
+
+
+def mps_to_discrete_function_nd(cores, ndims):
+    """`mps_to_discrete_function(Val(ndims), psi)` (reference src/function_to_mps.jl:140-145): sites j, j + ndims, ... belong to
+    dimension j; the result has one axis of 2^(n / ndims) points per dimension (first site = most significant bit)."""
+    n = len(cores)
+    assert n % ndims == 0
+    T = cores[0]
+    for c in cores[1:]:
+        T = np.tensordot(T, c, axes=([-1], [0]))
+    T = T.reshape((2,) * n)
+    perm = [j for d in range(ndims) for j in range(d, n, ndims)]
+    return np.transpose(T, perm).reshape((2 ** (n // ndims),) * ndims)
+
+
 def shift_mpo(A, a0, a1=1.0):
     """(a0 + a1 A) as an MPO by direct sum with the identity (reference examples/helmholtz_equation/helmholtz_equation.jl:122)."""
     n = len(A)
