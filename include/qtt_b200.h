@@ -92,8 +92,13 @@ typedef enum {
   QTT_SOLVER_SHIFT_INVERT = 2, /* `eigsolve_target` (reference src/eigsolve_target.jl:2-9): eigsolve(x -> linsolve(P, x, x, -target)) */
   QTT_SOLVER_DENSE_QR = 3,     /* `linsolve_pseudoinverse` (reference src/linsolve.jl:54-97): dense (4 chi^2)^2 operator, `qr!(T) \ b`;
                                   solves (a0 + a1 T) x = b -- pass a0 = 0, a1 = 1 for the reference's behaviour (it ignores them) */
-  QTT_SOLVER_DENSE_EIGEN = 4   /* `dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense Hermitian effective operator,
+  QTT_SOLVER_DENSE_EIGEN = 4,  /* `dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense Hermitian effective operator,
                                   eigenvector of the eigenvalue nearest `target`.  Dense kinds need 4 chi_l chi_r <= 8192. */
+  QTT_SOLVER_PG_LSQ = 5        /* `b_linsolve` (reference src/linsolve.jl:175-307, live solver `b_linsolve_exact_solver` :279-300):
+                                  Petrov-Galerkin sweep -- environments L.x.A.dag(b') with the right-hand side as the bra
+                                  (`ProjMPOLinsolve`, b re-orthogonalised to every bond, :248-253), local right-hand side `bvec`
+                                  (:255-261), dense SVD least squares `svd(A) \ b` on the (4 chi_b^2) x (4 chi_x^2) matrix.
+                                  a0 / a1 are ignored as in the reference body. */
 } qtt_solver_kind;
 
 typedef struct {

@@ -10,12 +10,12 @@ import numpy as np
 from ._lib import lib, check, default_context, SweepParams, SweepInfo, as_f, dptr
 from .chains import DeviceMPS, DeviceMPO
 
-__all__ = ["linsolve", "linsolve_pseudoinverse", "dmrg_target", "vec_to_mps", "function_to_mps", "apply_dft_mpo", "apply_idft_mpo",
+__all__ = ["linsolve", "linsolve_pseudoinverse", "b_linsolve", "dmrg_target", "vec_to_mps", "function_to_mps", "apply_dft_mpo", "apply_idft_mpo",
            "fourier_interpolation", "repeat_function", "apply", "add", "mps_to_vec", "sample", "prolongate", "retract", "multigrid_linsolve", "inner", "sqeuclidean", "sqeuclidean_normalized", "matvec2",
            "env_left", "env_right", "split2", "gemm", "krylov_op", "matvec2_flops", "env_flops",
-           "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN"]
+           "SOLVER_GMRES", "SOLVER_LANCZOS", "SOLVER_SHIFT_INVERT", "SOLVER_DENSE_QR", "SOLVER_DENSE_EIGEN", "SOLVER_PG_LSQ"]
 
-SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT, SOLVER_DENSE_QR, SOLVER_DENSE_EIGEN = 0, 1, 2, 3, 4
+SOLVER_GMRES, SOLVER_LANCZOS, SOLVER_SHIFT_INVERT, SOLVER_DENSE_QR, SOLVER_DENSE_EIGEN, SOLVER_PG_LSQ = 0, 1, 2, 3, 4, 5
 
 
 def _per_sweep(v, nsweeps, ctype, default):
@@ -93,6 +93,15 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
     if return_info:
         return out, [infos[i].as_dict() for i in range(p.nsweeps)]
     return out
+
+
+def b_linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, **kwargs):
+    """`b_linsolve(A, b, x0, a0=0, a1=1; kwargs...)` (reference src/linsolve.jl:263-307, live solver `b_linsolve_exact_solver`):
+    the two-site sweep with Petrov-Galerkin environments -- the right-hand side b is the BRA of the operator environments
+    (`ProjMPOLinsolve`, :175-253, b re-orthogonalised to every bond) -- and a dense SVD least-squares local solve on the
+    (4 chi_b^2) x (4 chi_x^2) projected operator with `bvec` (:255-261) as the right-hand side.  a0 / a1 are accepted and
+    ignored, as in the reference body."""
+    return linsolve(A, b, x0, 0.0, 1.0, nsweeps=nsweeps, maxdim=maxdim, mindim=mindim, cutoff=cutoff, _solver=SOLVER_PG_LSQ, **kwargs)
 
 
 def linsolve_pseudoinverse(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,

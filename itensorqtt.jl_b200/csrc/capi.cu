@@ -433,7 +433,7 @@ int qtt_linsolve(qtt_ctx* ctx, const qtt_mpo* A, const qtt_mps* b, qtt_mps* x, c
   QTT_REQUIRE(A->ctx == ctx && b->ctx == ctx && x->ctx == ctx, "chains belong to a different context");
   QTT_CUDA(cudaSetDevice(ctx->device));
   qtt_sweep_params P = *p;
-  if (P.solver != QTT_SOLVER_DENSE_QR) P.solver = QTT_SOLVER_GMRES;
+  if (P.solver != QTT_SOLVER_DENSE_QR && P.solver != QTT_SOLVER_PG_LSQ) P.solver = QTT_SOLVER_GMRES;
   two_site_sweeps(ctx, *A, b, *x, P, per_sweep);
   QTT_CATCH(ctx)
 }
@@ -445,7 +445,7 @@ int qtt_dmrg_target(qtt_ctx* ctx, const qtt_mpo* A, qtt_mps* psi, const qtt_swee
   QTT_CUDA(cudaSetDevice(ctx->device));
   qtt_sweep_params P = *p;
   if (P.solver == QTT_SOLVER_GMRES) P.solver = QTT_SOLVER_LANCZOS;
-  QTT_REQUIRE(P.solver != QTT_SOLVER_DENSE_QR, "qtt_dmrg_target: QTT_SOLVER_DENSE_QR is a linsolve solver");
+  QTT_REQUIRE(P.solver != QTT_SOLVER_DENSE_QR && P.solver != QTT_SOLVER_PG_LSQ, "qtt_dmrg_target: solver %d is a linsolve solver", P.solver);
   two_site_sweeps(ctx, *A, nullptr, *psi, P, per_sweep);
   QTT_CATCH(ctx)
 }

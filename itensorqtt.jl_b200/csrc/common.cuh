@@ -239,6 +239,12 @@ void dense_local_solve(Ctx* ctx, const double* L, const double* W12, const doubl
 // stats_dev[0..3] = (inverse-iteration steps, 1 - |<z_k, z_{k-1}>|, guarded pivots, max |R_ii|)
 void dense_local_eigen(Ctx* ctx, const double* L, const double* W12, const double* R, int chil, int chir, int wl, int wr, double target,
                        double* x_inout, double* scratch, int maxit, double* stats_dev);
+// `b_linsolve_exact_solver` (reference src/linsolve.jl:279-300): x = pinv(T) bT, T the (4 cbl cbr) x (4 chil chir) projected
+// operator with the right-hand side chain as the bra (L [wl][cbl][chil], R [wr][chir][cbr]); minimum-norm least squares through
+// the one-sided Jacobi SVD, singular values below eps max(m, N) sigma_1 dropped (LAPACK gelsd's default rcond).
+bool pg_local_ok(size_t rows, size_t cols);
+void pg_local_lstsq(Ctx* ctx, const double* L, const double* W12, const double* R, int cbl, int cbr, int chil, int chir, int wl, int wr,
+                    const double* bT, double* x);
 
 // ------------------------------------------------------------------ SVD split (svd_jacobi.cu)
 struct SplitResult {

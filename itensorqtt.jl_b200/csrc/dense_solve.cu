@@ -434,6 +434,75 @@ void build_op(Ctx* ctx, const double* L, const double* W12, const double* R, dou
 
 }  // namespace
 
+// ---- `b_linsolve` local solve: rectangular projected operator + SVD least squares ------------------------------------------
+namespace {
+// T[row][col], row = (a' t12 c') in the bra (= right-hand side) frame, col = (a s12 c) in the ket frame
+__global__ void dense_op_rect_kernel(const double* __restrict__ L, const double* __restrict__ W12, const double* __restrict__ R,
+                                     double* __restrict__ T, int cbl, int cbr, int chil, int chir, int wl, int wr) {
+  const long N = 4L * chil * chir;
+  const int row = blockIdx.y;
+  const int ap = row / (4 * cbr), t12 = (row / cbr) & 3, cp = row % cbr;
+  for (long col = blockIdx.x * (long)blockDim.x + threadIdx.x; col < N; col += (long)gridDim.x * blockDim.x) {
+    const int a = (int)(col / (4 * chir)), s12 = (int)((col / chir) & 3), c = (int)(col % chir);
+    double acc = 0.0;
+    for (int l = 0; l < wl; ++l) {
+      const double lv = L[((long)l * cbl + ap) * chil + a];
+      if (lv == 0.0) continue;
+      const double* w = W12 + (long)(l * 4 + s12) * (4 * wr) + t12 * wr;
+      double inner = 0.0;
+      for (int r = 0; r < wr; ++r) inner += w[r] * R[((long)r * chir + c) * cbr + cp];
+      acc += lv * inner;
+    }
+    T[(long)row * N + col] = acc;
+  }
+}
+// z_i <- z_i / sigma_i^2 for the singular values above rcond * sigma_1, 0 otherwise
+__global__ void pinv_scale_kernel(double* __restrict__ z, const double* __restrict__ sigma, int k, double rcond) {
+  const double smax = sigma[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    const double s = sigma[i];
+    z[i] = (s > rcond * smax && s > 0.0) ? z[i] / (s * s) : 0.0;
+  }
+}
+}  // namespace
+
+bool pg_local_ok(size_t rows, size_t cols) { return rows >= 1 && cols >= 1 && rows * cols <= (size_t)DENSE_LEN_MAX * DENSE_LEN_MAX / 4; }
+
+void pg_local_lstsq(Ctx* ctx, const double* L, const double* W12, const double* R, int cbl, int cbr, int chil, int chir, int wl, int wr,
+                    const double* bT, double* x) {
+  const int m = 4 * cbl * cbr;
+  const long N = 4L * chil * chir;
+  QTT_REQUIRE(pg_local_ok((size_t)m, (size_t)N), "b_linsolve: the dense local operator %d x %ld exceeds the cap", m, N);
+  double* T = ctx->arena.alloc((size_t)m * N);
+  const int kmax = m < N ? m : (int)N;
+  double* sigma = ctx->arena.alloc(kmax);
+  double* y = ctx->arena.alloc(N);
+  double* z = ctx->arena.alloc(kmax);
+  {
+    int gx = (int)((N + 255) / 256);
+    if (gx > 64) gx = 64;
+    dense_op_rect_kernel<<<dim3(gx, m), 256, 0, ctx->stream>>>(L, W12, R, T, cbl, cbr, chil, chir, wl, wr);
+    check_launch(ctx, "dense_op_rect");
+  }
+  // T = U S V^T: the rows of Wn are the right singular vectors of the non-zero singular values
+  RowSvd sv = svd_rows(ctx, T, m, (int)N, 0.0, 0, 1, sigma, 0);
+  GemmDesc g1;   // y = T^T b
+  g1.A = T; g1.B = bT; g1.C = y; g1.transA = true;
+  g1.M = (int)N; g1.N = 1; g1.K = m; g1.lda = N; g1.ldb = 1; g1.ldc = 1;
+  gemm(ctx, g1);
+  GemmDesc g2;   // z = V^T y
+  g2.A = sv.Wn; g2.B = y; g2.C = z;
+  g2.M = sv.k; g2.N = 1; g2.K = (int)N; g2.lda = N; g2.ldb = 1; g2.ldc = 1;
+  gemm(ctx, g2);
+  const double rcond = 2.220446049250313e-16 * (double)(m > N ? m : N);
+  pinv_scale_kernel<<<1, 256, 0, ctx->stream>>>(z, sigma, sv.k, rcond);
+  check_launch(ctx, "pinv_scale");
+  GemmDesc g3;   // x = V z
+  g3.A = sv.Wn; g3.B = z; g3.C = x; g3.transA = true;
+  g3.M = (int)N; g3.N = 1; g3.K = sv.k; g3.lda = N; g3.ldb = 1; g3.ldc = 1;
+  gemm(ctx, g3);
+}
+
 // QTT_DENSE_LEN_MAX (environment) lowers the cap, e.g. to bound the chi^4 memory of a batch of contexts
 bool dense_local_ok(size_t len) {
   size_t cap = DENSE_LEN_MAX;

@@ -397,6 +397,68 @@ void right_orthonormalize(Ctx* ctx, Mps& x) {
   }
 }
 
+// One step of `orthogonalize!(y, j)` on a device chain (un-truncated; bond dimensions as a QR would leave them).
+// forward: centre j-1 -> j (core j-1 becomes left-orthonormal); backward: centre j+1 -> j (core j+1 right-orthonormal).
+static void center_backward(Ctx* ctx, Mps& y, int j) {
+  const int jj = j + 1;
+  const int a = (int)y.chi[jj], c = (int)y.chi[jj + 1], ap = (int)y.chi[jj - 1];
+  ctx->ensure_arena((((size_t)4 * a * 2 * c + (size_t)2 * ap * a + 4096) * 2 + 65536) * sizeof(double));
+  size_t mark = ctx->arena.mark();
+  const int full = a < 2 * c ? a : 2 * c;
+  RowSvd r = svd_rows(ctx, y.core[jj].p, a, 2 * c, 0.0, 0, full, nullptr, 0);
+  const int k = r.k;
+  double* Rf = ctx->arena.alloc((size_t)a * k);
+  GemmDesc g;
+  g.A = y.core[jj].p; g.B = r.Wn; g.C = Rf; g.transB = true;
+  g.M = a; g.N = k; g.K = 2 * c; g.lda = 2 * c; g.ldb = 2 * c; g.ldc = k;
+  gemm(ctx, g);
+  double* Xn = ctx->arena.alloc((size_t)2 * ap * k);
+  GemmDesc h;
+  h.A = y.core[jj - 1].p; h.B = Rf; h.C = Xn;
+  h.M = 2 * ap; h.N = k; h.K = a; h.lda = a; h.ldb = k; h.ldc = k;
+  gemm(ctx, h);
+  dbuf_reserve(y.core[jj], (size_t)k * 2 * c);
+  dbuf_reserve(y.core[jj - 1], (size_t)2 * ap * k);
+  QTT_CUDA(cudaMemcpyAsync(y.core[jj].p, r.Wn, sizeof(double) * (size_t)k * 2 * c, cudaMemcpyDeviceToDevice, ctx->stream));
+  QTT_CUDA(cudaMemcpyAsync(y.core[jj - 1].p, Xn, sizeof(double) * (size_t)2 * ap * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  y.chi[jj] = k;
+  ctx->arena.release(mark);
+}
+
+static void center_forward(Ctx* ctx, Mps& y, int j) {
+  const int jj = j - 1;
+  const int a = (int)y.chi[jj], c = (int)y.chi[jj + 1], cn = (int)y.chi[jj + 2];
+  ctx->ensure_arena((((size_t)6 * a * 2 * c + (size_t)2 * c * cn + 4096) * 2 + 65536) * sizeof(double));
+  size_t mark = ctx->arena.mark();
+  // M = core[jj] as (2a x c); its transpose's row space gives Q^T: M = Q R, Q = Wn^T (2a x k), R = Wn M (k x c)
+  double* Mt = ctx->arena.alloc((size_t)c * 2 * a);
+  int64_t dims[2] = {2 * a, c};
+  int pm[2] = {1, 0};
+  permute(ctx, y.core[jj].p, Mt, 2, dims, pm);
+  const int full = c < 2 * a ? c : 2 * a;
+  RowSvd r = svd_rows(ctx, Mt, c, 2 * a, 0.0, 0, full, nullptr, 0);
+  const int k = r.k;
+  double* Rf = ctx->arena.alloc((size_t)k * c);
+  GemmDesc g;
+  g.A = r.Wn; g.B = y.core[jj].p; g.C = Rf;
+  g.M = k; g.N = c; g.K = 2 * a; g.lda = 2 * a; g.ldb = c; g.ldc = c;
+  gemm(ctx, g);
+  double* Xn = ctx->arena.alloc((size_t)k * 2 * cn);
+  GemmDesc h;
+  h.A = Rf; h.B = y.core[jj + 1].p; h.C = Xn;
+  h.M = k; h.N = 2 * cn; h.K = c; h.lda = c; h.ldb = 2 * cn; h.ldc = 2 * cn;
+  gemm(ctx, h);
+  double* Q = ctx->arena.alloc((size_t)2 * a * k);
+  int64_t dims2[2] = {k, 2 * a};
+  permute(ctx, r.Wn, Q, 2, dims2, pm);
+  dbuf_reserve(y.core[jj], (size_t)2 * a * k);
+  dbuf_reserve(y.core[jj + 1], (size_t)k * 2 * cn);
+  QTT_CUDA(cudaMemcpyAsync(y.core[jj].p, Q, sizeof(double) * (size_t)2 * a * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  QTT_CUDA(cudaMemcpyAsync(y.core[jj + 1].p, Xn, sizeof(double) * (size_t)k * 2 * cn, cudaMemcpyDeviceToDevice, ctx->stream));
+  y.chi[jj + 1] = k;
+  ctx->arena.release(mark);
+}
+
 // solver_kind: QTT_SOLVER_GMRES needs b; the eigen solvers ignore it.
 void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_sweep_params& P, qtt_sweep_info* infos) {
   const int n = A.n;
@@ -408,12 +470,13 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   if (b) QTT_REQUIRE(b->n == n && b->chi[0] == 1 && b->chi[n] == 1, "rhs MPS shape mismatch");
   QTT_REQUIRE(P.nsweeps >= 0, "nsweeps < 0");
   const bool dense_qr = (P.solver == QTT_SOLVER_DENSE_QR), dense_eig = (P.solver == QTT_SOLVER_DENSE_EIGEN);
-  const bool dense = dense_qr || dense_eig;
+  const bool pg = (P.solver == QTT_SOLVER_PG_LSQ);   // `b_linsolve`: Petrov-Galerkin environments, dense SVD least squares
+  const bool dense = dense_qr || dense_eig || pg;
   const bool fixed = !dense && P.fixed_matvecs > 0;
   const int kd = dense ? 1 : (fixed ? P.fixed_matvecs : P.krylovdim);
   QTT_REQUIRE(kd >= 1 && kd <= KD_MAX, "krylovdim must be in [1, %d]", KD_MAX);
   const int maxiter = P.maxiter > 0 ? P.maxiter : 1;
-  const bool is_lin = (P.solver == QTT_SOLVER_GMRES) || dense_qr;
+  const bool is_lin = (P.solver == QTT_SOLVER_GMRES) || dense_qr || pg;
   QTT_REQUIRE(is_lin || dense_eig || P.solver == QTT_SOLVER_LANCZOS || P.solver == QTT_SOLVER_SHIFT_INVERT, "unknown solver kind %d",
               P.solver);
   const bool shift_invert = (P.solver == QTT_SOLVER_SHIFT_INVERT);
@@ -435,6 +498,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
   QTT_CUDA(cudaEventCreate(&evs0));
   QTT_CUDA(cudaEventCreate(&evs1));
   std::vector<DBuf> LA(n + 1), RA(n + 1), LB(n + 1), RB(n + 1);
+  Mps bra;   // b_linsolve only
   auto cleanup = [&]() {
     for (auto* v : {&LA, &RA, &LB, &RB})
       for (auto& d : *v) dbuf_free(d);
@@ -447,21 +511,34 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
     auto t_call = std::chrono::steady_clock::now();
     QTT_CUDA(cudaEventRecord(evs0, ctx->stream));
     if (!P.x0_canonical) right_orthonormalize(ctx, x);
+    // `ProjMPOLinsolve` (reference src/linsolve.jl:175-253): a private copy of b, re-gauged to every bond, is the bra of the
+    // operator environments
+    if (pg) {
+      bra.ctx = ctx; bra.n = n; bra.dtype = QTT_F64; bra.chi = b->chi; bra.core.resize(n);
+      for (int j = 0; j < n; ++j) {
+        const size_t ne = (size_t)b->chi[j] * 2 * b->chi[j + 1];
+        dbuf_reserve(bra.core[j], ne);
+        QTT_CUDA(cudaMemcpyAsync(bra.core[j].p, b->core[j].p, ne * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      right_orthonormalize(ctx, bra);
+    }
     set_one(ctx, LA[0]);
     set_one(ctx, RA[n]);
-    if (b) { set_one(ctx, LB[0]); set_one(ctx, RB[n]); }
+    if (b && !pg) { set_one(ctx, LB[0]); set_one(ctx, RB[n]); }
     int wmax = 1;
     for (int j = 0; j <= n; ++j) wmax = wmax > (int)A.w[j] ? wmax : (int)A.w[j];
 
     auto update_right = [&](int j) {  // RA[j] from RA[j+1] and site j
       const int a = (int)x.chi[j], c = (int)x.chi[j + 1], w = (int)A.w[j], w2 = (int)A.w[j + 1];
-      ctx->ensure_arena((env_scratch(a, c, w, w2) + 4096) * sizeof(double) + ((size_t)8 * a * c + 4096) * sizeof(double));
+      const int ay = pg ? (int)bra.chi[j] : a, cy = pg ? (int)bra.chi[j + 1] : c;
+      const int am = a > ay ? a : ay, cm = c > cy ? c : cy;
+      ctx->ensure_arena((env_scratch(am, cm, w, w2) + 4096) * sizeof(double) + ((size_t)8 * am * cm + 4096) * sizeof(double));
       size_t mark = ctx->arena.mark();
-      double* scr = ctx->arena.alloc(env_scratch(a, c, w, w2));
-      dbuf_reserve(RA[j], (size_t)w * a * a);
-      env_right(ctx, RA[j + 1].p, x.core[j].p, A.core[j].p, x.core[j].p, RA[j].p, a, c, a, c, w, w2, scr);
+      double* scr = ctx->arena.alloc(env_scratch(am, cm, w, w2));
+      dbuf_reserve(RA[j], (size_t)w * a * ay);
+      env_right(ctx, RA[j + 1].p, x.core[j].p, A.core[j].p, pg ? bra.core[j].p : x.core[j].p, RA[j].p, a, c, ay, cy, w, w2, scr);
       ctx->arena.release(mark);
-      if (b) {
+      if (b && !pg) {
         const int ab = (int)b->chi[j], cb = (int)b->chi[j + 1];
         dbuf_reserve(RB[j], (size_t)ab * a);
         benv_right(ctx, RB[j + 1].p, x.core[j].p, b->core[j].p, RB[j].p, a, c, ab, cb);
@@ -469,13 +546,15 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
     };
     auto update_left = [&](int j) {  // LA[j+1] from LA[j] and site j
       const int a = (int)x.chi[j], c = (int)x.chi[j + 1], w = (int)A.w[j], w2 = (int)A.w[j + 1];
-      ctx->ensure_arena((env_scratch(a, c, w, w2) + 4096) * sizeof(double) + ((size_t)8 * a * c + 4096) * sizeof(double));
+      const int ay = pg ? (int)bra.chi[j] : a, cy = pg ? (int)bra.chi[j + 1] : c;
+      const int am = a > ay ? a : ay, cm = c > cy ? c : cy;
+      ctx->ensure_arena((env_scratch(am, cm, w, w2) + 4096) * sizeof(double) + ((size_t)8 * am * cm + 4096) * sizeof(double));
       size_t mark = ctx->arena.mark();
-      double* scr = ctx->arena.alloc(env_scratch(a, c, w, w2));
-      dbuf_reserve(LA[j + 1], (size_t)w2 * c * c);
-      env_left(ctx, LA[j].p, x.core[j].p, A.core[j].p, x.core[j].p, LA[j + 1].p, a, c, a, c, w, w2, scr);
+      double* scr = ctx->arena.alloc(env_scratch(am, cm, w, w2));
+      dbuf_reserve(LA[j + 1], (size_t)w2 * cy * c);
+      env_left(ctx, LA[j].p, x.core[j].p, A.core[j].p, pg ? bra.core[j].p : x.core[j].p, LA[j + 1].p, a, c, ay, cy, w, w2, scr);
       ctx->arena.release(mark);
-      if (b) {
+      if (b && !pg) {
         const int ab = (int)b->chi[j], cb = (int)b->chi[j + 1];
         dbuf_reserve(LB[j + 1], (size_t)cb * c);
         benv_left(ctx, LB[j].p, x.core[j].p, b->core[j].p, LB[j + 1].p, a, c, ab, cb);
@@ -499,12 +578,27 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
       for (int dir = 0; dir < 2; ++dir) {
         for (int step = 0; step < n - 1; ++step) {
           const int j = dir == 0 ? step : (n - 2 - step);
+          if (pg) {
+            // `position!(P::ProjMPOLinsolve, x, pos)` (reference src/linsolve.jl:248-253): b's orthogonality centre follows the
+            // bond; the left environment that contains the re-gauged core is rebuilt (the right ones only ever see
+            // right-orthonormal cores of b, which do not change)
+            if (dir == 0 && j > 0) {
+              center_forward(ctx, bra, j);
+              update_left(j - 1);
+            } else if (dir == 1 && j < n - 2) {
+              center_backward(ctx, bra, j);
+            }
+          }
           const int chil = (int)x.chi[j], chim = (int)x.chi[j + 1], chir = (int)x.chi[j + 2];
           const int wl = (int)A.w[j], wm = (int)A.w[j + 1], wr = (int)A.w[j + 2];
           const size_t len = (size_t)4 * chil * chir;
           size_t need = (len * (size_t)(2 * (kd + 1) + 16) + matvec2_scratch(chil, chir, wl, wr) + (size_t)16 * wl * wr + 65536) * sizeof(double);
           need += (size_t)256 * (kd + 24);
-          if (dense) {
+          if (pg) {
+            const size_t mrows = (size_t)4 * bra.chi[j] * bra.chi[j + 2];
+            QTT_REQUIRE(pg_local_ok(mrows, len), "b_linsolve: the dense local operator %zu x %zu exceeds the cap at bond %d", mrows, len, j);
+            need += ((size_t)6 * mrows * len + (size_t)32 * (len + mrows) + 262144) * sizeof(double);
+          } else if (dense) {
             QTT_REQUIRE(dense_local_ok(len), "dense local solver: 4 chi_l chi_r = %zu exceeds the cap (%d, QTT_DENSE_LEN_MAX) at bond %d; use a Krylov solver",
                         len, DENSE_LEN_MAX, j);
             need += (dense_scratch(len) + 64) * sizeof(double);
@@ -534,7 +628,17 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           const int kdl = (size_t)kd < len ? kd : (int)len;  // a Krylov space cannot exceed the local dimension
           {
             PhaseTimer pt(ctx, &info.t_krylov);
-            if (is_lin) {
+            if (pg) {
+              // `b_linsolve_exact_solver` (reference src/linsolve.jl:279-300): bT = `bvec(P)` (the two cores of b between the
+              // environments, :255-261), x = svd(T) \ bT on the rectangular projected operator
+              const int cbl = (int)bra.chi[j], cbm = (int)bra.chi[j + 1], cbr = (int)bra.chi[j + 2];
+              double* bT = ctx->arena.alloc((size_t)4 * cbl * cbr);
+              GemmDesc gb;
+              gb.A = bra.core[j].p; gb.B = bra.core[j + 1].p; gb.C = bT;
+              gb.M = 2 * cbl; gb.N = 2 * cbr; gb.K = cbm; gb.lda = cbm; gb.ldb = 2 * cbr; gb.ldc = 2 * cbr;
+              gemm(ctx, gb);
+              pg_local_lstsq(ctx, Lp, W12, Rp, cbl, cbr, chil, chir, wl, wr, bT, phi);
+            } else if (is_lin) {
               double* beff = ctx->arena.alloc(len);
               project_rhs(ctx, LB[j].p, b->core[j].p, b->core[j + 1].p, RB[j + 2].p, beff, chil, chir, (int)b->chi[j], (int)b->chi[j + 1],
                           (int)b->chi[j + 2]);
@@ -586,7 +690,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
               info.energy = st.theta;
             }
           }
-          if (fixed && is_lin && !small_pending && !dense_pending)
+          if (fixed && is_lin && !pg && !small_pending && !dense_pending)
             QTT_CUDA(cudaMemcpyAsync(ctx->h_scal + 70, ctx->d_scal + S_BETA, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
           if (!small_pending && !dense_pending) {
             info.matvecs += st.matvecs;
@@ -630,7 +734,7 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
             info.matvecs += (int64_t)mvs;
             info.flops_matvec += mvs * matvec_flops(chil, chir, wl, wm, wr);
             if (ctx->h_scal[73] > info.solver_resid) info.solver_resid = ctx->h_scal[73];
-          } else if (fixed && is_lin && ctx->h_scal[70] > info.solver_resid) {
+          } else if (fixed && is_lin && !pg && ctx->h_scal[70] > info.solver_resid) {
             info.solver_resid = ctx->h_scal[70];  // split2 synchronised
           }
           x.chi[j + 1] = sr.rank;
@@ -640,8 +744,11 @@ void two_site_sweeps(Ctx* ctx, const Mpo& A, const Mps* b, Mps& x, const qtt_swe
           {
             PhaseTimer pt(ctx, &info.t_env);
             // the environment past the turning point is never used (position! would not build it either)
-            if (dir == 0 && j < n - 2) update_left(j);
-            else if (dir == 1 && j > 0) update_right(j + 1);
+            if (dir == 0 && j < n - 2) {
+              if (!pg) update_left(j);   // b_linsolve: built at the next bond, after b's gauge has moved
+            } else if (dir == 1 && j > 0) {
+              update_right(j + 1);
+            }
           }
           if (trace) {
             fprintf(stderr, "[qtt trace] sweep %d dir %d bond %d chi (%d,%d,%d)->%d krylov %.3f ms svd %.3f ms (%d jacobi sweeps) env %.3f ms\n", sw, dir,

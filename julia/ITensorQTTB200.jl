@@ -57,6 +57,7 @@ const QTT_SOLVER_LANCZOS = Int32(1)
 const QTT_SOLVER_SHIFT_INVERT = Int32(2)   # `eigsolve_target` (reference src/eigsolve_target.jl:2-9) as the local solver
 const QTT_SOLVER_DENSE_QR = Int32(3)       # `linsolve_pseudoinverse` (reference src/linsolve.jl:54-97): dense operator, qr! \ b
 const QTT_SOLVER_DENSE_EIGEN = Int32(4)    # `dmrg_target` as written (reference src/dmrg_target.jl:1-12): dense Hermitian eigen
+const QTT_SOLVER_PG_LSQ = Int32(5)         # `b_linsolve` (reference src/linsolve.jl:175-307): Petrov-Galerkin sweep, dense SVD least squares
 
 struct QttError <: Exception
   code::Int
@@ -238,6 +239,16 @@ accepted and ignored (:67-92).  Local dimension 4 chi_l chi_r <= 8192; larger bo
 linsolve_pseudoinverse(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; tol=1e-5, krylovdim=20, maxiter=10,
                        ishermitian=false, reverse_step=false, nsite=2, kwargs...) =
   linsolve(A, b, x0, 0, 1; local_solver=QTT_SOLVER_DENSE_QR, kwargs...)
+
+"""
+    b_linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, mindim, cutoff, kwargs...)
+
+Reference src/linsolve.jl:263-307 (live solver `b_linsolve_exact_solver`): Petrov-Galerkin sweep with `b` as the bra of the
+operator environments (`ProjMPOLinsolve`, :175-253) and the dense SVD least-squares local solve `svd(A) \\ b`.  `a0`, `a1` are
+accepted and ignored, as in the reference body.
+"""
+b_linsolve(A::MPO, b::MPS, x0::MPS, a0::Number=0, a1::Number=1; reverse_step=false, kwargs...) =
+  linsolve(A, b, x0, 0, 1; local_solver=QTT_SOLVER_PG_LSQ, kwargs...)
 
 """
     dmrg_target(A::MPO, psi0::MPS; target_eigenvalue, nsweeps, maxdim, cutoff, ...)

@@ -192,3 +192,23 @@ def test_dense_solver_refuses_large_bonds(lib, monkeypatch):
     monkeypatch.setenv("QTT_DENSE_LEN_MAX", "256")
     with pytest.raises(Exception, match="dense local solver"):
         lib.linsolve_pseudoinverse(A, b, x0, nsweeps=1, maxdim=10, mindim=10, cutoff=0.0)
+
+
+@pytest.mark.parametrize("n,chi,nsw", [(3, 2, 1), (4, 3, 1), (8, 6, 2), (10, 8, 2)])
+def test_b_linsolve_parity(lib, n, chi, nsw):
+    """`b_linsolve` (reference src/linsolve.jl:263-307): Petrov-Galerkin environments with b as the bra, dense SVD least squares.
+    Same state as the oracle's restatement (numpy lstsq); the gauge of the re-orthogonalised b differs (Jacobi vs QR), which
+    the minimum-norm least-squares solution does not see."""
+    A, b, Am, bv = _airy(n)
+    x0 = O.random_mps(n, chi, 11)
+    kw = dict(nsweeps=nsw, maxdim=12, cutoff=1e-12)
+    xo, _ = O.b_linsolve(A, b, x0, **kw)
+    xg, info = lib.b_linsolve(A, b, x0, return_info=True, **kw)
+    assert O.linkdims(xg) == O.linkdims(xo)
+    assert O.fidelity_defect(xo, xg) <= 1e-9
+    assert info[-1]["maxlinkdim"] == max(O.linkdims(xg))
+    if n >= 4:
+        # the Petrov-Galerkin conditions are NOT the Galerkin ones: the two entry points must disagree on this system,
+        # i.e. the C-ABI really took the b_linsolve branch
+        xl = lib.linsolve(A, b, x0, **kw)
+        assert O.fidelity_defect(xl, xg) > 1e-3

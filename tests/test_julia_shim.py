@@ -119,7 +119,7 @@ def test_struct_mirrors_have_the_header_layout():
 def test_solver_constants_match_the_enum():
     enum = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"(QTT_SOLVER_\w+)\s*=\s*(\d+)", strip_comments(HDR)))
     consts = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"const (QTT_SOLVER_\w+) = Int32\((\d+)\)", JL))
-    assert enum == consts and len(enum) == 5
+    assert enum == consts and len(enum) == 6
 
 
 def body_of(fn):
