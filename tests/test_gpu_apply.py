@@ -188,3 +188,46 @@ def test_fourier_interpolation_and_repeat_function(lib, k):
     rep = dense(lib.repeat_function(psi, k, cutoff=1e-15))
     assert np.abs(rep - np.tile(f(x), 2 ** k)).max() < 5e-7
     assert np.abs(rep - dense(O.repeat_function(psi, k, cutoff=1e-15))).max() < 5e-7
+
+
+def _multi_sine(lib, n, nf, seed=3):
+    rng = np.random.default_rng(seed)
+    freqs = rng.choice(2 ** (n - 2), size=nf, replace=False).astype(np.int64) + 1
+    amps = rng.standard_normal(nf)
+    psi = O.mps_add_directsum(*[[c * (amps[i] if j == 0 else 1.0) for j, c in enumerate(O.qtt_sin(2 * np.pi * f, n))]
+                                for i, f in enumerate(freqs)])
+    return psi, freqs, amps
+
+
+@pytest.mark.parametrize("n,nf", [(16, 16), (20, 32)])
+def test_dft_apply_multi_frequency_vs_fft(lib, n, nf):
+    """BASELINE config 3's recipe below its full size (reference src/dft.jl:121-126, test/runtests.jl:249-274): the whole
+    spectrum of a sum of `nf` sines against numpy's FFT.  Tolerance 1e-6 norm-relative: the floor is the double-precision
+    phase 2 pi f x of the input construction (measured 4e-8)."""
+    psi, freqs, amps = _multi_sine(lib, n, nf)
+    got = lib.apply_dft_mpo(psi, cutoff=1e-15, maxdim=2 * nf)
+    f = dense(psi)
+    want = np.fft.fft(f) / 2 ** (n / 2)
+    g = dense(got)
+    assert np.linalg.norm(g - want) <= 1e-6 * np.linalg.norm(want)
+    assert max(O.linkdims(got)) <= 2 * nf
+
+
+def test_dft_apply_config3_full_size_analytic_spikes(lib):
+    """BASELINE config 3 at its full size (n = 30 sites, chi <= 128): the DFT of sum_i a_i sin(2 pi f_i x) is -i a_i sqrt(N)/2 at
+    k = f_i, +i a_i sqrt(N)/2 at k = N - f_i and zero elsewhere; the operator is unitary.  Sampled through `sample`."""
+    n, nf = 30, 64
+    N = 2 ** n
+    psi, freqs, amps = _multi_sine(lib, n, nf)
+    got = lib.apply_dft_mpo(psi, cutoff=1e-15, maxdim=2 * nf)
+    assert max(O.linkdims(got)) <= 2 * nf
+    spikes = np.concatenate([freqs, N - freqs])
+    want = np.concatenate([-0.5j * amps * np.sqrt(N), 0.5j * amps * np.sqrt(N)])
+    scale = np.abs(want).max()
+    assert np.abs(lib.sample(got, spikes) - want).max() <= 1e-6 * scale
+    rng = np.random.default_rng(5)
+    off = rng.integers(0, N, size=2048)
+    off = off[~np.isin(off, spikes)]
+    assert np.abs(lib.sample(got, off)).max() <= 1e-6 * scale
+    nin, nout = lib.inner(psi, psi), lib.inner(got, got)
+    assert abs(abs(nout) / abs(nin) - 1.0) <= 1e-9

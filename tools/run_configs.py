@@ -15,13 +15,12 @@ def sync():
 
 
 if "cfg3" in what:
-    import oracle as O   # DFT MPO builder (host set-up; the apply itself is the CUDA path)
     for n, nf in ((16, 16), (20, 32), (24, 64)):
         rng = np.random.default_rng(3)
         freqs = rng.choice(2 ** (n - 2), size=nf, replace=False) + 1
         amps = rng.standard_normal(nf)
         psi = q.mps_add_directsum(*[[c * (amps[i] if j == 0 else 1.0) for j, c in enumerate(q.qtt_sin(2 * np.pi * f, n))] for i, f in enumerate(freqs)])
-        t0 = time.perf_counter(); F = O.dft_mpo(n); t_build = time.perf_counter() - t0
+        t0 = time.perf_counter(); F = q.dft_mpo(n); t_build = time.perf_counter() - t0
         dpsi, dF = q.DeviceMPS(psi, ctx), q.DeviceMPO(F, ctx)
         out = q.apply(dF, dpsi, cutoff=1e-15, maxdim=2 * nf, on_device=True); sync()
         t0 = time.perf_counter()
@@ -32,7 +31,7 @@ if "cfg3" in what:
                "dft_mpo_build_host_s": t_build}
         if n <= 20:
             f = q.mps_to_discrete_function(psi)
-            got = q.mps_to_discrete_function(O.mps_reverse(out.download()))
+            got = q.mps_to_discrete_function([np.ascontiguousarray(np.transpose(c, (2, 1, 0))) for c in reversed(out.download())])
             want = np.fft.fft(f) / 2 ** (n / 2)
             rec["rel_err_vs_fft"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         print(json.dumps(rec), flush=True)
