@@ -1083,6 +1083,7 @@ __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
           if (tid == 0) s_any = 0;
           if (!__syncthreads_or(cand)) continue;
         }
+        if (a.dbg && tid == 0 && crank == 0 && sw < 64) atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 32 + sw, 1ull);
         lap(5);
         if (!intra) {
           // ---- 5a. cross round: B steps; step t pairs row a (P) with row B + (a + t) mod B (M).  Per step ONE barrier:
@@ -2076,8 +2077,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   a.eigen_mode = eigen_mode ? 1 : 0;
   a.dbg = nullptr;
   if (ctx->profiling && getenv("QTT_TRACE") != nullptr) {
-    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(32));
-    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 256, ctx->stream));
+    a.dbg = reinterpret_cast<long long*>(ctx->arena.alloc(96));   // [0, 32): phase counters; [32, 96): active slots per sweep
+    QTT_CUDA(cudaMemsetAsync(a.dbg, 0, 768, ctx->stream));
   }
   const int npairs = ((kmax + 1) & ~1) / 2;
   int grid = (npairs + 1) / 2;
@@ -2132,8 +2133,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     fprintf(stderr, "[qtt trace]   svd_rows_qr %d x %d: %s QR %.3f ms, numerical rank %d, jacobi %d sweeps %.3f ms\n", q, p,
             gs_done ? "Gram-Schmidt" : "Householder", msq, h_info[3], h_info[1], ms);
     if (a.dbg) {
-      long long h[32];
-      cudaMemcpy(h, a.dbg, 256, cudaMemcpyDeviceToHost);
+      long long h[96];
+      cudaMemcpy(h, a.dbg, 768, cudaMemcpyDeviceToHost);
       if (h[8] > 0 && h[15] > 0) {
         const char* nm[8] = {"busy", "load", "gram", "csync1", "reduce", "check", "inner", "apply"};
         fprintf(stderr, "[qtt trace]   per round over %lld CTAs, max / mean cycles:", h[15]);
@@ -2144,6 +2145,11 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
         fprintf(stderr, "[qtt trace]   gram jacobi CTA0 cycles per round: barrier %.0f load %.0f gram %.0f csync1 %.0f reduce %.0f check %.0f inner %.0f apply %.0f (%lld rounds)\n",
                 (double)h[0] / h[8], (double)h[1] / h[8], (double)h[2] / h[8], (double)h[3] / h[8], (double)h[4] / h[8], (double)h[5] / h[8],
                 (double)h[6] / h[8], (double)h[7] / h[8], h[8]);
+      if (h[8] > 0) {
+        fprintf(stderr, "[qtt trace]   block pairs with rotations per sweep:");
+        for (int k = 0; k < h_info[1] && k < 64; ++k) fprintf(stderr, " %lld", h[32 + k]);
+        fprintf(stderr, "\n");
+      }
       if (h[8] > 0) fprintf(stderr, "[qtt trace]   per round: look-ahead warp computing %.0f, waiting at the step barrier %.0f cycles\n", (double)h[9] / h[8], (double)h[10] / h[8]);
       else if (h[4] > 0)
         fprintf(stderr, "[qtt trace]   block jacobi CTA0 cycles per outer round: barrier %.0f load %.0f steps %.0f store %.0f (%lld rounds)\n",

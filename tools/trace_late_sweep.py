@@ -1,7 +1,10 @@
-"""Per-bond phase timings (QTT_TRACE) of one late sweep of the bench workload: python tools/trace_late_sweep.py [n chi nsweeps]"""
+"""Per-bond phase timings (QTT_TRACE) of the late sweeps of the bench workload: python tools/trace_late_sweep.py [n chi nsweeps [notrace]]
+(notrace: same sweeps without the trace counters, for ncu captures)."""
 import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["QTT_TRACE"] = "1"
+TRACE = not (len(sys.argv) > 4 and sys.argv[4] == "notrace")
+if TRACE:
+    os.environ["QTT_TRACE"] = "1"
 import oracle as O
 import itensorqtt_jl_b200 as lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
@@ -9,7 +12,7 @@ chi = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 nsw = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 nk = 18
 ctx = lib.default_context(0)
-ctx.set_profiling(True)
+ctx.set_profiling(TRACE)
 A = O.laplacian_mpo(n, 1.0)
 lam = -((2 * np.pi * (2.0 ** nk) / 2.0 ** n) ** 2)
 b = O.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
