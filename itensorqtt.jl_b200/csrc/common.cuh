@@ -79,6 +79,7 @@ struct Ctx {
   int64_t launches = 0;
   unsigned dense_epoch = 0;  // value of the dense-QR panel barrier counter (d_sync + 240)
   unsigned bar_epoch = 0;  // value of the fused-Krylov barrier counter (d_sync + 4) after the launches so far
+  unsigned gs_epoch = 0;   // value of the Gram-Schmidt select/re-orthogonalise barrier counter (d_sync + 232)
   int qr_last_rank = -1, qr_last_need = 0;  // numerical rank / mindim of the last split: picks the QR variant that goes first (svd_qr.cu)
   bool profiling = false;
   // small device scratch for scalars / flags / partial reductions

@@ -1506,6 +1506,189 @@ __global__ void __launch_bounds__(256) gs_select_kernel(const double* __restrict
   }
 }
 
+// Selection AND the second Gram-Schmidt pass of the selected rows in one cooperative launch (replaces gs_select + two skinny
+// GEMMs, 34 us per panel).  32 CTAs.  Every CTA repeats the selection and stages the <= 32 selected rows in shared memory; then
+//   phase 1   CTA b owns the basis rows j = b, b + 32, ...: coefficients C[j][u] = q_j . z_u for all 32 panel rows (global scratch);
+//   -- one grid barrier (32 CTAs) --
+//   phase 2   CTA b owns the columns [b cw, (b + 1) cw): Pbuf[u][c] = z_u[c] - sum_j C[j][u] q_j[c]  (C staged in shared memory).
+// Every coefficient comes from the un-updated row (classical Gram-Schmidt, as the GEMM pair did), sums run over j in order:
+// deterministic.  All CTAs always arrive at the barrier counter, so the host can advance its epoch by 32 per launch.
+__global__ void __launch_bounds__(256) gs_select_reorth_kernel(const double* __restrict__ Zw, int q, int p, int ldp, int rmax, double zero_tol2,
+                                                               int first, double thr_fixed, const double* __restrict__ norms,
+                                                               const int* __restrict__ rowstate, double* __restrict__ Pbuf, QrCtl* ctl,
+                                                               const double* __restrict__ Yq, int ldy, double* __restrict__ Cbuf,
+                                                               unsigned* bar, unsigned epoch, int pld) {
+  extern __shared__ __align__(16) double ssm[];
+  double* cand = ssm;                                   // [q rounded up to even]
+  double* Ps = ssm + ((q + 1) & ~1);                    // [GSB][pld] the selected rows; after the barrier: C^T [GSB][pld]
+  __shared__ int sel[GSB];
+  __shared__ double red[8];
+  __shared__ double s_thr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  auto arrive = [&]() {
+    __syncthreads();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(bar) : "memory");
+  };
+  const int r0 = ctl->r_next;
+  if (ctl->done) {
+    for (int c = tid; c < ldp; c += 256) Pbuf[(size_t)b * ldp + c] = 0.0;
+    arrive();
+    return;
+  }
+  double thr = thr_fixed > 0.0 ? thr_fixed : (first ? 0.0 : ctl->thr);
+  if (first && !(thr_fixed > 0.0)) {   // |Z|_F^2 once (the initial norms are the full row norms); same summation order in every CTA
+    double acc = 0.0;
+    for (int i = tid; i < q; i += 256) acc += norms[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int k = 0; k < 8; ++k) sum += red[k];
+      s_thr = zero_tol2 * sum;
+      if (b == 0) { ctl->F2 = sum; ctl->thr = s_thr; }
+    }
+    __syncthreads();
+    thr = s_thr;
+  }
+  int want = rmax - r0;
+  if (want > GSB) want = GSB;
+  if (tid < GSB) sel[tid] = -1;
+  for (int i = tid; i < q; i += 256) cand[i] = (rowstate[i] == 0) ? norms[i] : -1.0;
+  __syncthreads();
+  for (int i = tid; i < q; i += 256) {
+    const double ni = cand[i];
+    if (!(ni > thr)) continue;
+    int rank = 0;
+    for (int j = 0; j < q; ++j) {
+      const double nj = cand[j];
+      rank += (nj > ni) || (nj == ni && j < i);
+    }
+    if (rank < want) sel[rank] = i;   // ranks are distinct and dense among the rows above the threshold
+  }
+  __syncthreads();
+  if (b == 0 && tid == 0) {
+    int nsel = 0;
+    for (int k = 0; k < GSB; ++k) {
+      ctl->sel[k] = sel[k];
+      nsel += sel[k] >= 0;
+    }
+    ctl->r = r0;
+    ctl->nsel = nsel;
+    ctl->nbp = 0;
+  }
+  const int cpr = ldp / 2;   // double2 per row (ldp is even)
+  if (r0 == 0) {             // first panel: nothing to orthogonalise against
+    const int mine = sel[b];
+    for (int c = tid; c < cpr; c += 256) {
+      double2 v = make_double2(0.0, 0.0);
+      if (mine >= 0) v = *reinterpret_cast<const double2*>(Zw + (size_t)mine * ldp + 2 * c);
+      *reinterpret_cast<double2*>(Pbuf + (size_t)b * ldp + 2 * c) = v;
+    }
+    arrive();
+    return;
+  }
+  // ---- stage the selected rows and this CTA's basis rows (slot k = basis row b + 32 k); padded row stride pld (= 4 mod 16:
+  //      conflict-free DMMA fragment loads)
+  double* Qs = Ps + (size_t)GSB * pld;   // phase 1: [<= 16][pld] basis rows; phase 2: [r0][2 cw2] column slice of all basis rows
+  const int njb = r0 > b ? (r0 - b + GSB - 1) / GSB : 0;
+  for (int e = tid; e < GSB * cpr; e += 256) {
+    const int u = e / cpr, c = (e - u * cpr) * 2;
+    const int i = sel[u];
+    cp_async16(Ps + (size_t)u * pld + c, i >= 0 ? Zw + (size_t)i * ldp + c : Zw, i >= 0 ? 16 : 0);
+  }
+  for (int e = tid; e < njb * cpr; e += 256) {
+    const int k = e / cpr, c = (e - k * cpr) * 2;
+    cp_async16(Qs + (size_t)k * pld + c, Yq + (size_t)(b + GSB * k) * ldy + c, 16);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  const int g = lane >> 2, t4 = lane & 3;
+  // ---- phase 1 on the DMMA core: C[slot][u] = sum_c Qs[slot][c] Ps[u][c]; 2 x 4 tiles of 8 x 8, one per warp, K = ldp.
+  //      (A scalar version of the two phases was bound by shared-memory bandwidth: 43 us per launch against 13 us.)
+  {
+    const int mt = warp >> 2, nt = warp & 3;
+    if (mt * 8 < njb) {
+      const double* pa = Qs + (size_t)(mt * 8 + g) * pld + t4;
+      const double* pb = Ps + (size_t)(nt * 8 + g) * pld + t4;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+      const bool arow = mt * 8 + g < njb;   // slots beyond njb hold stale shared memory
+      int k0 = 0;
+      for (; k0 + 16 <= ldp; k0 += 16) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dmma884(a0[v], a1[v], arow ? pa[k0 + 4 * v] : 0.0, pb[k0 + 4 * v]);
+      }
+      for (; k0 < ldp; k0 += 4) {
+        const bool kin = k0 + t4 < ldp;
+        dmma884(a0[0], a1[0], (arow && kin) ? pa[k0] : 0.0, kin ? pb[k0] : 0.0);
+      }
+      const double v0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), v1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      if (arow) {   // transposed scratch: Cbuf[u][j], row stride pld
+        const int jj = b + GSB * (mt * 8 + g), u = nt * 8 + 2 * t4;
+        __stcg(Cbuf + (size_t)u * pld + jj, v0);
+        __stcg(Cbuf + (size_t)(u + 1) * pld + jj, v1);
+      }
+    }
+  }
+  // ---- this CTA's column slice of the selected rows: the C fragments of phase 2 (4 x NT tiles: rows u, columns of the slice)
+  const int cw2 = (cpr + GSB - 1) / GSB;   // double2 columns per CTA
+  const int cw = 2 * cw2, clo = b * cw;    // columns [clo, clo + cw) of the rows
+  const int NT = (cw + 7) / 8;             // <= 2 for ldp <= 512
+  const int mt2 = warp & 3, nt2 = warp >> 2;
+  const int xu = mt2 * 8 + g, xc = nt2 * 8 + 2 * t4;   // this lane's two entries: row xu, slice columns xc, xc + 1
+  const bool xok = nt2 < NT && xc < cw && clo + xc < ldp;
+  double x0 = 0.0, x1 = 0.0;
+  if (xok) {
+    const double2 v = *reinterpret_cast<const double2*>(Ps + (size_t)xu * pld + clo + xc);
+    x0 = v.x; x1 = v.y;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(bar) : "memory");
+    while ((int)(ld_acquire(bar) - (epoch + (unsigned)GSB)) < 0) {
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: X[u][c] -= sum_j C[j][u] q_j[c]; coefficient table [u][j] (stride pld) and the column slice of every basis row
+  //      into shared memory, then one 8 x 8 tile per warp, K = r0
+  double* Cs = Ps;
+  const int r0c = (r0 + 1) / 2;   // 16-byte chunks per coefficient row
+  for (int e = tid; e < GSB * r0c; e += 256) {
+    const int u = e / r0c, c = (e - u * r0c) * 2;
+    cp_async16(Cs + (size_t)u * pld + c, Cbuf + (size_t)u * pld + c, 16);
+  }
+  for (int e = tid; e < r0 * cw2; e += 256) {
+    const int jj = e / cw2, c2 = e % cw2;
+    const bool ok = clo + 2 * c2 < ldp;
+    cp_async16(Qs + (size_t)jj * cw + 2 * c2, ok ? Yq + (size_t)jj * ldy + clo + 2 * c2 : Yq, ok ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  if (nt2 < NT) {
+    const double* pa = Cs + (size_t)(mt2 * 8 + g) * pld + t4;     // A[g][t4] = C^T[u][j]
+    const int bc = nt2 * 8 + g;                                      // B[t4][g] = Qs[j][bc]
+    const bool bok = bc < cw;
+    const double* pb = Qs + (size_t)t4 * cw + (bok ? bc : 0);
+    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    int k0 = 0;
+    for (; k0 + 16 <= r0; k0 += 16) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dmma884(a0[v], a1[v], pa[k0 + 4 * v], bok ? pb[(size_t)(k0 + 4 * v) * cw] : 0.0);
+    }
+    for (; k0 < r0; k0 += 4) {
+      const bool kin = k0 + t4 < r0;
+      dmma884(a0[0], a1[0], kin ? pa[k0] : 0.0, (kin && bok) ? pb[(size_t)k0 * cw] : 0.0);
+    }
+    if (xok) {
+      const double v0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), v1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      *reinterpret_cast<double2*>(Pbuf + (size_t)xu * ldp + clo + xc) = make_double2(x0 - v0, x1 - v1);
+    }
+  }
+}
+
 // CholeskyQR + Newton-Schulz of the (re-orthogonalised) panel Pbuf: accepted rows become new orthonormal basis rows, written
 // (compacted, zero rows behind them); the panel rows go back to Zw so that the update GEMMs see them.
 __global__ void __launch_bounds__(GST) gs_panel_kernel(const double* __restrict__ Pbuf, int p, int ldp, int pld, int rmax,
@@ -1920,10 +2103,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
       set_smem(gs_update_kernel<8>, 200 * 1024);
       set_smem(gs_update_kernel<16>, 200 * 1024);
       set_smem(gs_update_kernel<24>, 200 * 1024);
+      set_smem(gs_select_reorth_kernel, 216 * 1024);
     });
     double* Zw = SE;   // the (q + p) x ldp Householder workspace is free on this path
     double* Pbuf = ctx->arena.alloc((size_t)GSB * ldp);
     double* C2 = ctx->arena.alloc((size_t)(kmax + GSB) * GSB);
+    double* Ct = ctx->arena.alloc((size_t)GSB * pld);   // coefficients of the fused re-orthogonalisation, [u][j]
     QTT_CUDA(cudaMemsetAsync(Y, 0, sizeof(double) * (size_t)(kmax + GSB) * ldy, ctx->stream));
     {
       int grid = (q + 7) / 8;
@@ -1939,10 +2124,31 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     // panels over the working rows W (nrows x ldp) until `rmax` basis rows exist or nothing above the threshold is left
     auto run_panels = [&](double* W, int nrows, double* nrm, int* rst, int rmax, int r_have, bool main_phase, double thr_fixed) -> bool {
       const int nominal = (rmax - r_have + GSB - 1) / GSB;
+      // fused selection + second Gram-Schmidt pass (one cooperative launch of 32 CTAs) when its staging fits in shared memory
+      const int cw2 = (ldp / 2 + GSB - 1) / GSB;
+      const size_t qs_d = std::max((size_t)((kmax + GSB - 1) / GSB) * pld, (size_t)kmax * 2 * cw2);
+      const size_t fsm = sizeof(double) * ((size_t)((nrows + 1) & ~1) + (size_t)GSB * pld + qs_d);
+      static const bool fused_off = getenv("QTT_GS_FUSED") != nullptr && atoi(getenv("QTT_GS_FUSED")) == 0;
+      const bool fused = !fused_off && fsm <= 216 * 1024 && kmax <= ldp && ldp <= 512;
       for (int pn = 0; pn < nominal + 16; ++pn) {
+        if (fused) {
+          const double* Wc = W; const double* nc = nrm; const int* rc = rst; const double* yq = Y + qd;
+          double zt2 = zt * zt;
+          int first = (main_phase && pn == 0) ? 1 : 0;
+          unsigned* bar = ctx->d_sync + 232;
+          unsigned epoch = ctx->gs_epoch;
+          int nr = nrows, pp = p, lp = ldp, rm = rmax, ly = ldy;
+          double tf = thr_fixed;
+          int pl = pld;
+          void* args[] = {&Wc, &nr, &pp, &lp, &rm, &zt2, &first, &tf, &nc, &rc, &Pbuf, &ctl, &yq, &ly, &Ct, &bar, &epoch, &pl};
+          QTT_CUDA(cudaLaunchCooperativeKernel((void*)gs_select_reorth_kernel, dim3(GSB), dim3(256), args, fsm, ctx->stream));
+          ctx->launches++;
+          ctx->gs_epoch += (unsigned)GSB;
+        } else {
         launch_pdl(ctx, "gs_select", gs_select_kernel, dim3(GSB), dim3(256), sizeof(double) * nrows, (const double*)W, nrows, p, ldp, rmax, zt * zt,
                    (main_phase && pn == 0) ? 1 : 0, thr_fixed, (const double*)nrm, (const int*)rst, Pbuf, ctl);
-        if (pn > 0 || r_have > 0) {
+        }
+        if (!fused && (pn > 0 || r_have > 0)) {
           int J = r_have + pn * GSB;   // upper bound of the basis rows so far (rows beyond r are zero)
           if (J > kmax) J = kmax;
           GemmDesc g1;   // C2 (J x 32) = Q (J x p) . Pbuf^T
