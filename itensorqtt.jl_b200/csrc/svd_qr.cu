@@ -1991,6 +1991,102 @@ __global__ void __launch_bounds__(256) gs_update_kernel(double* __restrict__ Zw,
   }
 }
 
+// The same update on the DMMA core, 8 working rows per CTA (64 CTAs at q = 512 instead of 32, and no shared-memory bandwidth
+// wall: the scalar version re-reads the 32 basis rows for every pair of working rows).  C = Z Q1^T (8 x 32, K = ldp: four
+// 8 x 8 tiles, the K range halved between two warps each), then Z -= C Q1 (64 column tiles, K = 32), norms from the fragments.
+// Fixed summation orders throughout.  Shared memory: Q1 [32][pld], Z [8][pld], C halves [2][8][36].
+constexpr int GUR = 8;   // working rows per CTA
+__global__ void __launch_bounds__(256) gs_update_mma_kernel(double* __restrict__ Zw, int q, int p, int ldp, int pld,
+                                                            const int* __restrict__ rowstate, double* __restrict__ norms,
+                                                            double* __restrict__ Y, int qd, int ldy, int write_r, const QrCtl* ctl) {
+  dev::pdl_wait();
+  extern __shared__ __align__(16) double usm[];
+  const int na = ctl->nbp;
+  if (na == 0) return;
+  const int r0 = ctl->r;
+  double* Qs = usm;                          // [GSB][pld]
+  double* Zs = Qs + (size_t)GSB * pld;       // [GUR][pld]
+  double* Ch = Zs + (size_t)GUR * pld;       // [2][GUR][36] partial coefficients of the two K halves; [0] becomes the sum
+  __shared__ double nrm_s[8][GUR];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i0 = blockIdx.x * GUR;
+  const int cpr = ldp / 2;
+  for (int e = tid; e < GSB * cpr; e += 256) {
+    const int t = e / cpr, c = (e - t * cpr) * 2;
+    const bool ok = t < na;
+    cp_async16(Qs + (size_t)t * pld + c, ok ? Y + (size_t)(r0 + t) * ldy + qd + c : Y, ok ? 16 : 0);
+  }
+  for (int e = tid; e < GUR * cpr; e += 256) {
+    const int il = e / cpr, c = (e - il * cpr) * 2;
+    const bool ok = i0 + il < q;
+    cp_async16(Zs + (size_t)il * pld + c, ok ? Zw + (size_t)(i0 + il) * ldp + c : Zw, ok ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  // ---- C = Z Q1^T: warp -> (n-tile nt = warp & 3, K half kh = warp >> 2)
+  {
+    const int nt = warp & 3, kh = warp >> 2;
+    const int kspan = (((ldp + 1) / 2) + 3) & ~3;   // per half, multiple of 4
+    const int kb = kh * kspan, ke = min(ldp, kb + kspan);
+    const double* pa = Zs + (size_t)g * pld + t4;
+    const double* pb = Qs + (size_t)(nt * 8 + g) * pld + t4;
+    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    int k0 = kb;
+    for (; k0 + 16 <= ke; k0 += 16) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dmma884(a0[v], a1[v], pa[k0 + 4 * v], pb[k0 + 4 * v]);
+    }
+    for (; k0 < ke; k0 += 4) {
+      const bool kin = k0 + t4 < ke;
+      dmma884(a0[0], a1[0], kin ? pa[k0] : 0.0, kin ? pb[k0] : 0.0);
+    }
+    double* dst = Ch + (size_t)kh * GUR * 36 + g * 36 + nt * 8 + 2 * t4;
+    dst[0] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    dst[1] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+  }
+  __syncthreads();
+  {
+    const int il = tid >> 5, t = tid & 31;   // 8 x 32 coefficients
+    const double c = Ch[il * 36 + t] + Ch[GUR * 36 + il * 36 + t];
+    __syncthreads();
+    Ch[il * 36 + t] = c;
+    if (write_r && t < na && i0 + il < q) Y[(size_t)(r0 + t) * ldy + i0 + il] = c;   // rows of R: Y[r0 + t][i] = z_i . q_t
+  }
+  __syncthreads();
+  // ---- Z -= C Q1: warp takes the column tiles warp, warp + 8, ...; K = 32
+  double nacc = 0.0;   // this lane's share of |z_g|^2
+  double ca[GSB / 4];
+#pragma unroll
+  for (int ks = 0; ks < GSB / 4; ++ks) ca[ks] = Ch[g * 36 + ks * 4 + t4];   // A fragments: C[g][k]
+  for (int tile = warp; tile * 8 < ldp; tile += 8) {
+    const int n0 = tile * 8;
+    double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int ks = 0; ks < GSB / 4; ++ks) {
+      const double bv = (n0 + g < ldp) ? Qs[(size_t)(ks * 4 + t4) * pld + n0 + g] : 0.0;
+      dmma884(d0[ks & 1], d1[ks & 1], ca[ks], bv);
+    }
+    const int c = n0 + 2 * t4;
+    if (c < ldp) {
+      const double2 z = *reinterpret_cast<const double2*>(Zs + (size_t)g * pld + c);
+      const double v0 = z.x - (d0[0] + d0[1]), v1 = z.y - (d1[0] + d1[1]);
+      if (i0 + g < q) *reinterpret_cast<double2*>(Zw + (size_t)(i0 + g) * ldp + c) = make_double2(v0, v1);
+      nacc += v0 * v0 + v1 * v1;
+    }
+  }
+  nacc += __shfl_xor_sync(0xffffffffu, nacc, 1);
+  nacc += __shfl_xor_sync(0xffffffffu, nacc, 2);
+  if (t4 == 0) nrm_s[warp][g] = nacc;
+  __syncthreads();
+  if (tid < GUR && i0 + tid < q) {
+    double n = 0.0;
+    for (int w = 0; w < 8; ++w) n += nrm_s[w][tid];
+    if (rowstate[i0 + tid] == 0) norms[i0 + tid] = n;
+  }
+}
+
 __global__ void gs_commit_kernel(QrCtl* ctl, int reopen) {
   dev::pdl_wait();
   if (threadIdx.x == 0) {
@@ -2104,6 +2200,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
       set_smem(gs_update_kernel<16>, 200 * 1024);
       set_smem(gs_update_kernel<24>, 200 * 1024);
       set_smem(gs_select_reorth_kernel, 216 * 1024);
+      set_smem(gs_update_mma_kernel, 216 * 1024);
     });
     double* Zw = SE;   // the (q + p) x ldp Householder workspace is free on this path
     double* Pbuf = ctx->arena.alloc((size_t)GSB * ldp);
@@ -2167,7 +2264,12 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
           if (ug > ctx->sms) ug = ctx->sms;
           const size_t usm = sizeof(double) * (size_t)GSB * ldp;
           const int wr = main_phase ? 1 : 0;
-          if (ldp <= 256) launch_pdl(ctx, "gs_update", gs_update_kernel<8>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
+          const size_t msm = sizeof(double) * ((size_t)(GSB + GUR) * pld + 2 * GUR * 36);
+          static const bool mma_off = getenv("QTT_GS_UPDATE") != nullptr && std::string(getenv("QTT_GS_UPDATE")) == "scalar";
+          if (!mma_off && msm <= 216 * 1024)
+            launch_pdl(ctx, "gs_update", gs_update_mma_kernel, dim3((nrows + GUR - 1) / GUR), dim3(256), msm, W, nrows, p, ldp, pld, (const int*)rst, nrm, Y, qd,
+                       ldy, wr, (const QrCtl*)ctl);
+          else if (ldp <= 256) launch_pdl(ctx, "gs_update", gs_update_kernel<8>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
           else if (ldp <= 512) launch_pdl(ctx, "gs_update", gs_update_kernel<16>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
           else launch_pdl(ctx, "gs_update", gs_update_kernel<24>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
         }
