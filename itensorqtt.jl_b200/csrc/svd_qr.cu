@@ -1883,6 +1883,205 @@ __global__ void __launch_bounds__(GST) gs_panel_kernel(const double* __restrict_
   }
 }
 
+// The panel factorisation spread over ONE CLUSTER of 8 CTAs (the single-CTA kernel above is bound by the FP64 rate of one SM:
+// the two Gram matrices and the two 32 x 32 x p products are 33 k of its 75 k cycles).  CTA c owns the columns
+// [c cwid, (c + 1) cwid) of the panel; partial Gram matrices are all-gathered through distributed shared memory and summed in rank
+// order by every CTA (bit-identical copies), the 32 x 32 Cholesky / inverse / Newton-Schulz matrices are computed redundantly.
+constexpr int GPC = 8;      // CTAs per cluster
+__global__ void __launch_bounds__(GST) gs_panel_cluster_kernel(const double* __restrict__ Pbuf, int p, int ldp, int cwid, int rmax,
+                                                               double* __restrict__ Zw, int* __restrict__ rowstate, double* __restrict__ Yq,
+                                                               int ldy, double thr_fixed, QrCtl* ctl) {
+  dev::pdl_wait();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  extern __shared__ __align__(16) double psm[];
+  const int sld = cwid + 4;                 // row stride of the slice (cwid is a multiple of 16: = 4 mod 16)
+  double* P = psm;                          // [GSB][sld] this CTA's column slice of the panel
+  double* Gs = P + (size_t)GSB * sld;       // [GSB][GSB + 1] Gram matrix, then L
+  double* T = Gs + GSB * (GSB + 1);         // [GSB][GSB + 4] compacted L^-1 D^-1, then the Newton-Schulz matrix; Lm behind it
+  double* STG = T + GSB * (GSB + 4) + GSB * (GSB + 1);   // [2][GPC][640] all-gather staging of the upper-triangular Gram tiles
+  __shared__ double dn[GSB], sc[GSB], invd[GSB];
+  __shared__ int acc[GSB], slot[GSB];
+  __shared__ int s_na;
+  constexpr int TLD = GSB + 4;
+  constexpr int UTE = 10 * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bool done = ctl->done != 0;
+  const int nsel = done ? 0 : ctl->nsel;
+  if (nsel == 0) {   // nothing above the zero threshold is left (or the basis is complete): the update kernel becomes a no-op
+    if (crank == 0 && tid == 0) { ctl->done = 1; ctl->nbp = 0; }
+    return;
+  }
+  cluster.sync();    // every CTA of the cluster runs before the first distributed-shared-memory store
+  const int r0 = ctl->r;
+  const double thr = thr_fixed > 0.0 ? thr_fixed : ctl->thr;
+  const int c0 = crank * cwid;              // first global column of the slice
+  const int wcols = max(0, min(cwid, ldp - c0));   // valid columns (even)
+  // ---- load the slice; the re-orthogonalised rows replace the working rows
+  {
+    const int cpr = cwid / 2;
+    for (int e = tid; e < GSB * cpr; e += GST) {
+      const int u = e / cpr, c = (e - u * cpr) * 2;
+      const bool ok = c < wcols;
+      cp_async16(P + (size_t)u * sld + c, ok ? Pbuf + (size_t)u * ldp + c0 + c : Pbuf, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    if (tid < GSB) slot[tid] = ctl->sel[tid];   // (slot[] is reused: the row indices of the panel)
+    __syncthreads();
+    for (int e = tid; e < GSB * cpr; e += GST) {   // the working rows take the re-orthogonalised values
+      const int u = e / cpr, c = (e - u * cpr) * 2;
+      const int i = slot[u];
+      if (i >= 0 && c < wcols) *reinterpret_cast<double2*>(Zw + (size_t)i * ldp + c0 + c) = *reinterpret_cast<const double2*>(P + (size_t)u * sld + c);
+    }
+  }
+  // ---- Gram matrix of the panel: partial over the slice (DMMA, 10 upper-triangular tiles), all-gather, sum in rank order
+  auto gram_allreduce = [&](int buf) {
+    if (warp < 10) {
+      int ti = 0, rem = warp;
+      while (rem >= 4 - ti) { rem -= 4 - ti; ++ti; }
+      const int tj = ti + rem;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* pa = P + (size_t)(ti * 8 + g) * sld + t4;
+      const double* pb = P + (size_t)(tj * 8 + g) * sld + t4;
+      for (int k0 = 0; k0 < cwid; k0 += 16) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dmma884(a0[v], a1[v], pa[k0 + 4 * v], pb[k0 + 4 * v]);
+      }
+      const double2 v = make_double2((a0[0] + a0[1]) + (a0[2] + a0[3]), (a1[0] + a1[1]) + (a1[2] + a1[3]));
+      double* base = STG + (size_t)buf * GPC * UTE + (size_t)crank * UTE + warp * 64 + g * 8 + 2 * t4;
+      for (int k = 0; k < GPC; ++k) *reinterpret_cast<double2*>(cluster.map_shared_rank(base, k)) = v;
+    }
+    cluster.sync();
+    const double* stg = STG + (size_t)buf * GPC * UTE;
+    for (int e = tid; e < UTE; e += GST) {
+      double sum = 0.0;
+      for (int k = 0; k < GPC; ++k) sum += stg[k * UTE + e];
+      const int tl = e >> 6, within = e & 63;
+      int ti = 0, rem = tl;
+      while (rem >= 4 - ti) { rem -= 4 - ti; ++ti; }
+      const int tj = ti + rem;
+      const int i = ti * 8 + (within >> 3), j = tj * 8 + (within & 7);
+      Gs[i * (GSB + 1) + j] = sum;
+      Gs[j * (GSB + 1) + i] = sum;
+    }
+    __syncthreads();
+  };
+  gram_allreduce(0);
+  // ---- squared norms (the diagonal), scales, scaled Gram matrix
+  if (tid < GSB) {
+    const double a = Gs[tid * (GSB + 1) + tid];
+    dn[tid] = a;
+    sc[tid] = (tid < nsel && a > thr) ? rsqrt(a) : 0.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < GSB * GSB; e += GST) {
+    const int i = e / GSB, j = e % GSB;
+    Gs[i * (GSB + 1) + j] *= sc[i] * sc[j];
+  }
+  __syncthreads();
+  // ---- Cholesky with deferral, all 512 threads (as in gs_panel_kernel)
+  {
+    constexpr int LD = GSB + 1;
+    double* Lm = T + GSB * TLD;          // [32][33] the Cholesky factor (zero columns for deferred / null rows)
+    const int j = tid & 31, i0 = tid >> 5, i1 = i0 + 16;
+    for (int t = 0; t < GSB; ++t) {
+      const double piv = Gs[t * LD + t];
+      const bool ok = sc[t] > 0.0 && piv > GS_DEFER;
+      const double inv = ok ? rsqrt(piv) : 0.0, inv2 = inv * inv;
+      const double gjt = Gs[j * LD + t];
+      const double g0 = Gs[i0 * LD + t], g1 = Gs[i1 * LD + t];
+      if (j == t) {
+        Lm[i0 * LD + t] = i0 >= t ? g0 * inv : 0.0;
+        Lm[i1 * LD + t] = i1 >= t ? g1 * inv : 0.0;
+        if (i0 == 0) { invd[t] = inv; acc[t] = ok ? 1 : 0; }
+      }
+      __syncthreads();
+      if (j > t) {
+        if (i0 > t) Gs[i0 * LD + j] -= g0 * gjt * inv2;
+        if (i1 > t) Gs[i1 * LD + j] -= g1 * gjt * inv2;
+      }
+      __syncthreads();
+    }
+    double s0 = 0.0, s1 = 0.0;
+    double* X = Gs;
+    for (int t = 0; t < GSB; ++t) {
+      if (i0 == t) X[t * LD + j] = (((t == j && acc[j]) ? 1.0 : 0.0) - s0) * invd[t];
+      if (i1 == t) X[t * LD + j] = (((t == j && acc[j]) ? 1.0 : 0.0) - s1) * invd[t];
+      __syncthreads();
+      const double xt = X[t * LD + j];
+      if (i0 > t) s0 += Lm[i0 * LD + t] * xt;
+      if (i1 > t) s1 += Lm[i1 * LD + t] * xt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int na = 0;
+      for (int t = 0; t < GSB; ++t) { slot[t] = na; na += acc[t]; }
+      s_na = na;
+    }
+    __syncthreads();
+    const double x0v = X[i0 * LD + j], x1v = X[i1 * LD + j];
+    __syncthreads();
+    for (int e = tid; e < GSB * TLD; e += GST) T[e] = 0.0;
+    __syncthreads();
+    if (acc[i0]) T[slot[i0] * TLD + j] = x0v * sc[j];
+    if (acc[i1]) T[slot[i1] * TLD + j] = x1v * sc[j];
+  }
+  __syncthreads();
+  const int na = s_na;
+  // ---- slice <- T slice (32 x 32 times 32 x cwid on the DMMA core; a warp owns 8-column strips, so P is updated in place)
+  auto apply_t = [&]() {
+    for (int strip = warp; strip < cwid / 8; strip += GST / 32) {
+      const int n0 = strip * 8;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k0 = 0; k0 < GSB; k0 += 4) {
+        const double bv = P[(size_t)(k0 + t4) * sld + n0 + g];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) dmma884(a0[mt], a1[mt], T[(mt * 8 + g) * TLD + k0 + t4], bv);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) *reinterpret_cast<double2*>(P + (size_t)(mt * 8 + g) * sld + n0 + 2 * t4) = make_double2(a0[mt], a1[mt]);
+    }
+  };
+  apply_t();
+  __syncthreads();
+  // ---- one Newton-Schulz step: Q1 <- (1.5 I - 0.5 Q1 Q1^T) Q1
+  gram_allreduce(1);
+  for (int e = tid; e < GSB * GSB; e += GST) {
+    const int i = e / GSB, j = e % GSB;
+    T[i * TLD + j] = (i < na && j < na) ? ((i == j ? 1.5 : 0.0) - 0.5 * Gs[i * (GSB + 1) + j]) : 0.0;
+  }
+  __syncthreads();
+  apply_t();
+  __syncthreads();
+  // ---- results: the new basis rows go straight into the carried part of Y = [R | Q^T] (rows r0 ... r0 + na - 1)
+  {
+    const int cpr = cwid / 2;
+    for (int e = tid; e < na * cpr; e += GST) {
+      const int u = e / cpr, c = (e - u * cpr) * 2;
+      if (c >= wcols) continue;
+      double2 v = make_double2(0.0, 0.0);
+      if (c0 + c < p) v = *reinterpret_cast<const double2*>(P + (size_t)u * sld + c);
+      *reinterpret_cast<double2*>(Yq + (size_t)(r0 + u) * ldy + c0 + c) = v;
+    }
+  }
+  if (crank == 0) {
+    if (tid < GSB && tid < nsel) {
+      const int i = ctl->sel[tid];
+      if (i >= 0 && (acc[tid] || !(dn[tid] > thr))) rowstate[i] = 1;   // accepted, or numerically in the span already
+    }
+    if (tid == 0) {
+      ctl->nbp = na;
+      ctl->r_next = r0 + na;
+      ctl->serial = ctl->serial + 1;
+      if (r0 + na >= rmax) ctl->done = 1;
+    }
+  }
+}
+
 // Right-looking update of the working rows against the panel's basis rows Q1 (<= 32, in shared memory):
 //   c_t = z_i . q_t (all t from the same z_i: the rows of Q1 are orthonormal to rounding), z_i <- z_i - sum_t c_t q_t,
 // the new residual norm, and the coefficients straight into Y[r0 + t][i] (rows of R).  A warp owns TWO rows at a time so that every
@@ -2201,6 +2400,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
       set_smem(gs_update_kernel<24>, 200 * 1024);
       set_smem(gs_select_reorth_kernel, 216 * 1024);
       set_smem(gs_update_mma_kernel, 216 * 1024);
+      set_smem(gs_panel_cluster_kernel, 200 * 1024);
     });
     double* Zw = SE;   // the (q + p) x ldp Householder workspace is free on this path
     double* Pbuf = ctx->arena.alloc((size_t)GSB * ldp);
@@ -2257,6 +2457,25 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
           g2.M = GSB; g2.N = p; g2.K = J; g2.lda = GSB; g2.ldb = ldy; g2.ldc = ldp; g2.alpha = -1.0; g2.beta = 1.0;
           gemm(ctx, g2);
         }
+        static const bool pc_off = getenv("QTT_GS_PANEL") != nullptr && std::string(getenv("QTT_GS_PANEL")) == "single";
+        if (!pc_off && !gs_dbg) {
+          const int cwid = (((ldp + GPC - 1) / GPC) + 15) & ~15;
+          const size_t csm = sizeof(double) * ((size_t)GSB * (cwid + 4) + 2 * GSB * (GSB + 1) + GSB * (GSB + 4) + (size_t)2 * GPC * 640);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(GPC);
+          cfg.blockDim = dim3(GST);
+          cfg.dynamicSmemBytes = csm;
+          cfg.stream = ctx->stream;
+          cudaLaunchAttribute at[2];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = GPC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = 2;
+          cudaError_t e = cudaLaunchKernelEx(&cfg, gs_panel_cluster_kernel, (const double*)Pbuf, p, ldp, cwid, rmax, W, rst, Y + qd, ldy, thr_fixed, ctl);
+          if (e != cudaSuccess) fail(QTT_ERR_CUDA, "gs_panel_cluster launch failed: %s", cudaGetErrorString(e));
+          ctx->launches++;
+        } else
         launch_pdl(ctx, "gs_panel", gs_panel_kernel, dim3(1), dim3(GST), gs_smem, (const double*)Pbuf, p, ldp, pld, rmax, W, rst, Y + qd, ldy, thr_fixed, ctl,
                    gs_dbg);
         {   // coefficients of every row on the new basis rows (= rows of R), W <- W - C^T Q1, fresh residual norms
