@@ -15,6 +15,7 @@
 // doubles: conflict-free LDS.64 fragment loads) and zero-fill ragged edges, so edge bonds take the same path.
 #include "common.cuh"
 #include <cstdlib>
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 namespace qtt {
 namespace {
@@ -423,6 +424,328 @@ __global__ void __launch_bounds__(256) matvec_b_kernel(MvBArgs p) {
   }
 }
 
+// ---- K_B with TMA-staged tiles -------------------------------------------------------------------------------------------
+// Same tile shape, warp layout, in-CTA split-K and epilogue as matvec_b_kernel<2, 64>; the operand tiles are fetched by
+// `cp.async.bulk.tensor` (SASS UTMALDG) issued by ONE thread and tracked by mbarrier transaction counts instead of 256 threads
+// issuing LDGSTS.  Layouts that keep the m8n8k4 fragment loads at the two-wavefront minimum WITHOUT padding (a tensor-map box
+// cannot be padded):
+//   A tile (32 rows x 16 k, 128-byte rows): one box with the 128-byte swizzle: element (r, c) sits at chunk (c >> 1) ^ (r & 7);
+//   B tile (16 k x 64 columns): eight boxes of 16 rows x 8 columns (64-byte rows, no swizzle): the four k rows of a fragment
+//   start 64 bytes apart, so the 32 lanes of a warp cover every bank exactly twice.
+// Out-of-range rows / columns / k are zero-filled by the TMA unit (edge bonds need no predicates).
+constexpr int TMB_ST = 6;
+constexpr int TMB_A_BYTES = 32 * BK * 8;        // 4096
+constexpr int TMB_B_BYTES = BK * 64 * 8;        // 8192
+constexpr int TMB_STAGE = TMB_A_BYTES + TMB_B_BYTES;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, unsigned bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+
+struct MvBTmaArgs {
+  double* C;
+  int M, N, K;
+  long ldc;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+// 9 warps: warps 0-7 compute (two K-groups of 2 x 2 warps, as in matvec_b_kernel), warp 8 is the TMA producer.  Stage s holds
+// k-tile kt with kt % 6 == s, so even stages always belong to K-group 0 and odd ones to K-group 1: the groups run decoupled, each
+// stage has a `full` barrier (transaction count) and an `empty` barrier (one arrival per consumer warp of its group); there is no
+// CTA-wide barrier in the main loop.
+__global__ void __launch_bounds__(288) matvec_b_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                           MvBTmaArgs p) {
+  constexpr int BM = 32, BN = 64, NJ = BN / 16;
+  extern __shared__ __align__(16) unsigned char raw[];
+  // the 128-byte swizzle atom is 1024 bytes: align the stage buffers by hand (the dynamic segment is only 16-byte aligned by contract)
+  const unsigned base = (smem_u32(raw) + 1023u) & ~1023u;
+  unsigned char* sbuf = raw + (base - smem_u32(raw));
+  __shared__ __align__(8) unsigned long long full[TMB_ST], empty[TMB_ST];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kg = (warp >> 2) & 1;     // K-group of a compute warp
+  const int w4 = warp & 3;
+  const int wm0 = (w4 >> 1) * 16, wn0 = (w4 & 1) * (BN / 2);
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (tid == 0) {
+    for (int s = 0; s < TMB_ST; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int KT = (p.K + BK - 1) / BK;
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");  // T2 is produced by the preceding matvec_a grid
+
+  double acc[2][NJ][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int st = kt % TMB_ST, use = kt / TMB_ST;
+        if (use > 0) mbar_wait(smem_u32(&empty[st]), (unsigned)(use - 1) & 1u);
+        const unsigned bar = smem_u32(&full[st]);
+        const unsigned dstA = base + st * TMB_STAGE, dstB = dstA + TMB_A_BYTES;
+        mbar_expect_tx(bar, TMB_STAGE);
+        tma_load_2d(dstA, &tmA, bar, kt * BK, m0);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) tma_load_2d(dstB + b * 1024, &tmB, bar, n0 + 8 * b, kt * BK);
+      }
+    }
+  } else {
+    // fragment offsets (doubles) inside a stage
+    int a_off[2][BK / 4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) a_off[i][kk] = (wm0 + i * 8 + g) * BK + ((((kk * 2 + (t >> 1)) ^ g) << 1) | (t & 1));
+    const int b_off = (wn0 >> 3) * 128 + t * 8 + g;
+    for (int kt = kg; kt < KT; kt += 2) {
+      const int st = kt % TMB_ST;
+      mbar_wait(smem_u32(&full[st]), (unsigned)(kt / TMB_ST) & 1u);
+      const double* as = reinterpret_cast<const double*>(sbuf + st * TMB_STAGE);
+      const double* bs = reinterpret_cast<const double*>(sbuf + st * TMB_STAGE + TMB_A_BYTES) + b_off;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[2], b[NJ];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = as[a_off[i][kk]];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) b[j] = bs[j * 128 + kk * 32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&empty[st]));
+    }
+  }
+  __syncthreads();
+  // combine the two K-groups: group 1 parks its tile in shared memory, group 0 adds (fixed order) and stores
+  double* red = reinterpret_cast<double*>(sbuf);  // [4 warps][2][NJ][32 lanes] double2
+  if (warp < 8 && kg == 1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        *reinterpret_cast<double2*>(red + (((w4 * 2 + i) * NJ + j) * 32 + lane) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+  }
+  __syncthreads();
+  if (warp < 8 && kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = m0 + wm0 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const double2 o = *reinterpret_cast<const double2*>(red + (((w4 * 2 + i) * NJ + j) * 32 + lane) * 2);
+        const double v0 = acc[i][j][0] + o.x, v1 = acc[i][j][1] + o.y;
+        const int col = n0 + wn0 + j * 8 + 2 * t;
+        if (row < p.M && col < p.N) {
+          double* cp = p.C + (size_t)row * p.ldc + col;
+          if (col + 1 < p.N) *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+          else cp[0] = v0;
+        }
+      }
+    }
+  }
+}
+
+// ---- K_A with TMA-staged tiles: the 4-warp 16 x 16 shape of matvec_a_kernel<WL, 1, 2, 2, 2> plus a producer warp.
+// Two 3-D boxes per k-tile: L as {k, a', w} with box {16, 16, WL} (all w slices of the (a' block, k-tile) in one copy) and v as
+// {c, s, k} with box {16, 4, 16}; both have 128-byte rows and the 128-byte swizzle (fragment loads at the two-wavefront minimum).
+constexpr int TMA_ST = 4;
+template <int WL>
+__global__ void __launch_bounds__(160) matvec_a_tma_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmV,
+                                                           MvAArgs p) {
+  constexpr int BA = 16, BC = 16;
+  constexpr int A_BYTES = WL * BA * BK * 8, B_BYTES = BK * 4 * BC * 8, STAGE = A_BYTES + B_BYTES;
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle atoms");
+  extern __shared__ __align__(16) unsigned char raw[];
+  const unsigned base = (smem_u32(raw) + 1023u) & ~1023u;
+  unsigned char* sbuf = raw + (base - smem_u32(raw));
+  double* Ws = reinterpret_cast<double*>(sbuf + TMA_ST * STAGE);   // W12 [4 wl][4 wr]
+  __shared__ __align__(8) unsigned long long full[TMA_ST], empty[TMA_ST];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wa0 = (warp >> 1) * 8, wc0 = (warp & 1) * 8;
+  const int a0 = blockIdx.x * BA, c0 = blockIdx.y * BC;
+  const int wr = p.wr, chil = p.chil, chir = p.chir;
+  if (tid == 0) {
+    for (int s = 0; s < TMA_ST; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  asm volatile("griddepcontrol.launch_dependents;\n" ::);
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  for (int i = tid; i < 16 * WL * wr; i += 160) Ws[i] = p.W12[i];
+  __syncthreads();
+  const int KT = (chil + BK - 1) / BK;
+  double acc[WL][4][2];
+#pragma unroll
+  for (int w = 0; w < WL; ++w)
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg) acc[w][sg][0] = acc[w][sg][1] = 0.0;
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int st = kt % TMA_ST, use = kt / TMA_ST;
+        if (use > 0) mbar_wait(smem_u32(&empty[st]), (unsigned)(use - 1) & 1u);
+        const unsigned bar = smem_u32(&full[st]);
+        const unsigned dstA = base + st * STAGE, dstB = dstA + A_BYTES;
+        mbar_expect_tx(bar, STAGE);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                     ::"r"(dstA), "l"(&tmL), "r"(bar), "r"(kt * BK), "r"(a0), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                     ::"r"(dstB), "l"(&tmV), "r"(bar), "r"(c0), "r"(0), "r"(kt * BK) : "memory");
+      }
+    }
+  } else {
+    int a_off[BK / 4], b_off[BK / 4][4];
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      a_off[kk] = (wa0 + g) * BK + ((((kk * 2 + (t >> 1)) ^ g) << 1) | (t & 1));
+#pragma unroll
+      for (int sg = 0; sg < 4; ++sg) {
+        const int rho = (kk * 4 + t) * 4 + sg;
+        b_off[kk][sg] = rho * 16 + (((((wc0 + g) >> 1) ^ (rho & 7)) << 1) | (g & 1));
+      }
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+      const int st = kt % TMA_ST;
+      mbar_wait(smem_u32(&full[st]), (unsigned)(kt / TMA_ST) & 1u);
+      const double* as = reinterpret_cast<const double*>(sbuf + st * STAGE);
+      const double* bs = reinterpret_cast<const double*>(sbuf + st * STAGE + A_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[WL], b[4];
+#pragma unroll
+        for (int w = 0; w < WL; ++w) a[w] = as[w * BA * BK + a_off[kk]];
+#pragma unroll
+        for (int sg = 0; sg < 4; ++sg) b[sg] = bs[b_off[kk][sg]];
+#pragma unroll
+        for (int w = 0; w < WL; ++w)
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) dmma884(acc[w][sg][0], acc[w][sg][1], a[w], b[sg]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&empty[st]));
+    }
+    // epilogue: this lane owns (a' = a0 + wa0 + g, c = c0 + wc0 + 2t, 2t+1) for every (w, s12)
+    const int gc = c0 + wc0 + 2 * t;
+    const int ga = a0 + wa0 + g;
+    if (gc < chir && ga < chil) {
+      const int nout = 4 * wr;
+      for (int o = 0; o < nout; ++o) {  // o = (t12, wr)
+        double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < WL; ++w)
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) {
+            const double c = Ws[(w * 4 + sg) * nout + o];
+            o0 += c * acc[w][sg][0];
+            o1 += c * acc[w][sg][1];
+          }
+        *reinterpret_cast<double2*>(p.T2 + ((size_t)ga * nout + o) * chir + gc) = make_double2(o0, o1);   // chir is even on this path
+      }
+    }
+  }
+}
+
+typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmEncodeFn tm_encoder() {
+  static TmEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) f = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<TmEncodeFn>(f);
+  }();
+  return fn;
+}
+// row-major rows x cols FP64 matrix, box = brows x bcols
+bool tm_make(CUtensorMap* tm, const double* ptr, long rows, long cols, long ld, int brows, int bcols, bool swizzle128) {
+  TmEncodeFn enc = tm_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)bcols, (cuuint32_t)brows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// FP64 tensor {d0 (contiguous), d1, d2} with byte strides s1, s2 and box {b0, b1, b2}, 128-byte swizzle (b0 * 8 == 128)
+bool tm_make3(CUtensorMap* tm, const double* ptr, long d0, long d1, long d2, long s1, long s2, int b0, int b1, int b2) {
+  TmEncodeFn enc = tm_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)s1, (cuuint64_t)s2};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int WL>
+bool launch_mva_tma(Ctx* ctx, const MvAArgs& a) {
+  struct TmCache { const double* L = nullptr; const double* v = nullptr; int chil = 0, chir = 0; CUtensorMap tl, tv; bool ok = false; };
+  static thread_local TmCache tc;
+  if (!(tc.ok && tc.L == a.L && tc.v == a.v && tc.chil == a.chil && tc.chir == a.chir)) {
+    tc.ok = tm_make3(&tc.tl, a.L, a.chil, a.chil, WL, (long)a.chil * 8, (long)a.chil * a.chil * 8, BK, 16, WL) &&
+            tm_make3(&tc.tv, a.v, a.chir, 4, a.chil, (long)a.chir * 8, (long)4 * a.chir * 8, 16, 4, BK);
+    tc.L = a.L; tc.v = a.v; tc.chil = a.chil; tc.chir = a.chir;
+  }
+  if (!tc.ok) return false;
+  constexpr size_t smem = (size_t)TMA_ST * (WL * 16 * BK * 8 + BK * 4 * 16 * 8) + 1024 + 16 * WL * 8 * sizeof(double);
+  static DevOnce once;
+  once.run(ctx->device, [&] {
+    QTT_CUDA(cudaFuncSetAttribute(matvec_a_tma_kernel<WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.chil + 15) / 16, (a.chir + 15) / 16);
+  cfg.blockDim = dim3(160);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool pdl = !(getenv("QTT_PDL") && atoi(getenv("QTT_PDL")) == 0);
+  cfg.numAttrs = pdl ? 1 : 0;
+  QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_a_tma_kernel<WL>, tc.tl, tc.tv, a));
+  check_launch(ctx, "matvec_a_tma");
+  return true;
+}
+
 template <int WL, int MI, int WM, int WN>
 constexpr size_t mva_smem() {
   return (size_t)(STAGES * (WL * 8 * MI * WM * (BK + 4) + BK * (4 * 8 * WN + 4)) + 16 * WL * 8) * sizeof(double);
@@ -440,7 +763,7 @@ void launch_mva(Ctx* ctx, const MvAArgs& a) {
   launch_pdl(ctx, "matvec_a", kern, grid, dim3(WM * WN * 32), smem, a);
 }
 
-int g_mva_shape = -1;  // QTT_MVA_SHAPE: tuning override (0: 8 warps 32x16, 1: 4 warps 16x16, 2: 4 warps MI=2 32x16)
+int g_mva_shape = -1;  // QTT_MVA_SHAPE: tuning override (0: 8 warps 32x16, 1: 4 warps 16x16)
 
 template <int WL, int VEC>
 void launch_mva_shape(Ctx* ctx, const MvAArgs& a) {
@@ -454,9 +777,11 @@ void launch_mva_shape(Ctx* ctx, const MvAArgs& a) {
     const bool one_full_wave = big * 10 > (long)ctx->sms * 2 * 9 && big <= (long)ctx->sms * 2;
     shape = one_full_wave ? 0 : 1;
   }
+  // (a third shape, 4 warps with two 16-row fragments each, spilled 10-15 KB of registers at w_l >= 5 and never won: removed)
+  static const int tma_env = getenv("QTT_MVA_TMA") ? atoi(getenv("QTT_MVA_TMA")) : 1;   // QTT_MVA_TMA=0: the cp.async kernel (A/B runs)
+  if (tma_env && shape == 1 && VEC == 2 && a.wr <= 8 && tm_encoder() && launch_mva_tma<WL>(ctx, a)) return;
   if (shape == 0) launch_mva<WL, 1, 4, 2, VEC>(ctx, a);
-  else if (shape == 1) launch_mva<WL, 1, 2, 2, VEC>(ctx, a);
-  else launch_mva<WL, 2, 2, 2, VEC>(ctx, a);
+  else launch_mva<WL, 1, 2, 2, VEC>(ctx, a);
 }
 
 template <int VEC>
@@ -526,6 +851,31 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
     cfg.attrs = attr;
     static const bool pdl = !(getenv("QTT_PDL") && atoi(getenv("QTT_PDL")) == 0);
     cfg.numAttrs = pdl ? 1 : 0;
+    // TMA-staged variant of the 32 x 64 kernel (default; A/B in profiles/r02_matvec_tma.md): needs 16-byte global strides
+    static const int tma_env = getenv("QTT_MVB_TMA") ? atoi(getenv("QTT_MVB_TMA")) : 1;   // QTT_MVB_TMA=0: the cp.async kernel (A/B runs)
+    if (tma_env && bn == 64 && vecB && (b.lda % 2 == 0) && (b.ldb % 2 == 0) && tm_encoder()) {
+      // the two tensor maps depend on the operand addresses and shape only: one-entry cache (31 matvecs per bond share them)
+      struct TmCache { const double* A = nullptr; const double* B = nullptr; int M = 0, N = 0, K = 0; long lda = 0, ldb = 0; CUtensorMap ta, tb; bool ok = false; };
+      static thread_local TmCache tc;
+      if (!(tc.ok && tc.A == b.A && tc.B == b.B && tc.M == b.M && tc.N == b.N && tc.K == b.K && tc.lda == b.lda && tc.ldb == b.ldb)) {
+        tc.ok = tm_make(&tc.ta, b.A, b.M, b.K, b.lda, 32, BK, true) && tm_make(&tc.tb, b.B, b.K, b.N, b.ldb, BK, 8, false);
+        tc.A = b.A; tc.B = b.B; tc.M = b.M; tc.N = b.N; tc.K = b.K; tc.lda = b.lda; tc.ldb = b.ldb;
+      }
+      if (tc.ok) {
+        static DevOnce once_t;
+        once_t.run(ctx->device, [&] {
+          QTT_CUDA(cudaFuncSetAttribute(matvec_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
+        });
+        const size_t need = (size_t)TMB_ST * TMB_STAGE + 1024;
+        cfg.dynamicSmemBytes = (ctas64 <= ctx->sms && smemB_max > need) ? smemB_max : need;
+        cfg.blockDim = dim3(288);
+        MvBTmaArgs ta;
+        ta.C = b.C; ta.M = b.M; ta.N = b.N; ta.K = b.K; ta.ldc = b.ldc;
+        QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_tma_kernel, tc.ta, tc.tb, ta));
+        check_launch(ctx, "matvec_b_tma");
+        return;
+      }
+    }
     if (bn == 32) {
       if (vecB) QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<2, 32>, b));
       else QTT_CUDA(cudaLaunchKernelEx(&cfg, matvec_b_kernel<1, 32>, b));
