@@ -853,7 +853,8 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
     cfg.numAttrs = pdl ? 1 : 0;
     // TMA-staged variant of the 32 x 64 kernel (default; A/B in profiles/r02_matvec_tma.md): needs 16-byte global strides
     static const int tma_env = getenv("QTT_MVB_TMA") ? atoi(getenv("QTT_MVB_TMA")) : 1;   // QTT_MVB_TMA=0: the cp.async kernel (A/B runs)
-    if (tma_env && bn == 64 && vecB && (b.lda % 2 == 0) && (b.ldb % 2 == 0) && tm_encoder()) {
+    // (single-wave grids only: with several CTAs per SM the 64-byte B boxes lose to cp.async, chi = 384: 24.4 vs 28.2 TFLOP/s)
+    if (tma_env && bn == 64 && ctas64 <= ctx->sms && vecB && (b.lda % 2 == 0) && (b.ldb % 2 == 0) && tm_encoder()) {
       // the two tensor maps depend on the operand addresses and shape only: one-entry cache (31 matvecs per bond share them)
       struct TmCache { const double* A = nullptr; const double* B = nullptr; int M = 0, N = 0, K = 0; long lda = 0, ldb = 0; CUtensorMap ta, tb; bool ok = false; };
       static thread_local TmCache tc;
@@ -867,7 +868,7 @@ void matvec2_fused(Ctx* ctx, const double* L, const double* W12, const double* R
           QTT_CUDA(cudaFuncSetAttribute(matvec_b_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB_max));
         });
         const size_t need = (size_t)TMB_ST * TMB_STAGE + 1024;
-        cfg.dynamicSmemBytes = (ctas64 <= ctx->sms && smemB_max > need) ? smemB_max : need;
+        cfg.dynamicSmemBytes = smemB_max > need ? smemB_max : need;   // one CTA per SM (see the padding note above)
         cfg.blockDim = dim3(288);
         MvBTmaArgs ta;
         ta.C = b.C; ta.M = b.M; ta.N = b.N; ta.K = b.K; ta.ldc = b.ldc;
