@@ -246,9 +246,9 @@ def run_ours(args):
                 "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                 # from profiles/matvec_traffic.json (the ncu capture it was read from is named there); algorithmic operand bytes 7.3 MB
                 "traffic": traffic,
-                "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_kernel (L.v DMMA GEMM + W12 register epilogue) + "
-                          "matvec_b_kernel (T2.R DMMA GEMM, in-CTA split-K), the pair timed back to back with CUDA events on "
-                          "the library's stream" % chi,
+                "kernel": "two-site matvec L.W1.W2.R.psi at chi=%d, w=3 = matvec_a_tma_kernel (L.v DMMA GEMM + W12 register epilogue) + "
+                          "matvec_b_tma_kernel (T2.R DMMA GEMM, in-CTA split-K), operand tiles staged by TMA (cp.async.bulk.tensor + "
+                          "mbarrier pipelines); the pair timed back to back with CUDA events on the library's stream" % chi,
                 # the sweep's matvec flops expressed in full-size launches x the measured launch time (edge / mid bonds run
                 # smaller, less efficient launches, so this is a lower bound; the ncu launch list gives the kernel pair's share directly)
                 "share_of_step": infos[-1]["flops_matvec"] / f_mv * mv_ms / ms_per_step,
