@@ -192,6 +192,9 @@ def run_ours(args):
     e2e_kw = dict(nsweeps=1, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov, x0_canonical=True, ctx=ctx,
                   return_info=True, host_order="F")
     xo = hx
+    # results land in pinned buffers as well (two sets, alternating: step i reads the set step i-1 wrote); bond dimensions are
+    # fixed under this protocol (mindim = maxdim), so the shapes never change
+    hout = [pinned_fortran_copy(hx), pinned_fortran_copy(hx)]
     if e2e_steps:
         # one untimed pass of the same call on the start state: first-use costs of the host path (device blocks entering
         # the caching allocator, pinned staging) are warm-up, exactly like the W warm-up steps of the device-resident leg
@@ -203,7 +206,7 @@ def run_ours(args):
         flush.zero_()
         torch.cuda.synchronize()
         ts = time.perf_counter()
-        xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, **e2e_kw)
+        xo, _ = q.linsolve(hA, hb, hx, -lam, 1.0, out=hout[i % 2], **e2e_kw)
         e2e_list.append((time.perf_counter() - ts) * 1e3)
         hx = xo
     barrier()

@@ -64,12 +64,13 @@ def _params(nsweeps, maxdim, mindim, cutoff, solver, a0, a1, tol, krylovdim, max
 
 def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, tol=1e-5, krylovdim=20,
              maxiter=10, ishermitian=False, normalize=False, outputlevel=0, fixed_matvecs=None, x0_canonical=False,
-             ctx=None, return_info=False, on_device=False, host_order="C", _solver=SOLVER_GMRES):
+             ctx=None, return_info=False, on_device=False, host_order="C", out=None, _solver=SOLVER_GMRES):
     """`linsolve(A::MPO, b::MPS, x0::MPS, a0=0, a1=1; nsweeps, maxdim, cutoff, tol, krylovdim, maxiter, ishermitian)`
     -- solves (a0 + a1 A) x = b by two-site sweeps with a local GMRES
     (reference examples/airy_equation/src/linsolve.jl:24-34; call sites airy_equation.jl:429, src/eigsolve_target.jl:4).
     `ishermitian` is accepted for signature compatibility (KrylovKit still picks GMRES unless isposdef).
-    A, b, x0: lists of host cores or Device* handles.  Returns host cores (or a DeviceMPS if `on_device`)."""
+    A, b, x0: lists of host cores or Device* handles.  Returns host cores (or a DeviceMPS if `on_device`).  `out`: caller-owned
+    column-major host buffers (e.g. pinned) that receive the result, see `DeviceMPS.download`."""
     ctx = ctx or default_context()
     dA, fa = _as_dev_mpo(A, ctx)
     db, fb = _as_dev_mps(b, ctx)
@@ -87,12 +88,14 @@ def linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cu
             dA.free()
         if fb:
             db.free()
-    out = dx if on_device else dx.download(order=host_order)
-    if not on_device:
-        dx.free()
+    try:
+        res = dx if on_device else dx.download(order=host_order, out=out)
+    finally:
+        if not on_device:
+            dx.free()
     if return_info:
-        return out, [infos[i].as_dict() for i in range(p.nsweeps)]
-    return out
+        return res, [infos[i].as_dict() for i in range(p.nsweeps)]
+    return res
 
 
 def b_linsolve(A, b, x0, a0=0, a1=1, *, nsweeps=None, maxdim=None, mindim=None, cutoff=None, **kwargs):

@@ -212,3 +212,20 @@ def test_b_linsolve_parity(lib, n, chi, nsw):
         # i.e. the C-ABI really took the b_linsolve branch
         xl = lib.linsolve(A, b, x0, **kw)
         assert O.fidelity_defect(xl, xg) > 1e-3
+
+
+def test_linsolve_into_caller_buffers(lib):
+    """`out=`: the result is written into caller-owned column-major buffers (pinned memory in bench.py's end-to-end leg);
+    same bits as the plain call, wrong shapes are rejected."""
+    n = 8
+    A, b, Am, bv = _airy(n)
+    x0 = O.random_mps(n, 4, 5)
+    kw = dict(nsweeps=2, maxdim=8, mindim=8, cutoff=0.0, tol=1e-12, krylovdim=20, maxiter=4)
+    ref = lib.linsolve(A, b, x0, host_order="F", **kw)
+    out = [np.empty(c.shape, dtype=np.float64, order="F") for c in ref]
+    got = lib.linsolve(A, b, x0, host_order="F", out=out, **kw)
+    assert all(g is o for g, o in zip(got, out))
+    assert all(np.array_equal(g, r) for g, r in zip(got, ref))
+    bad = [np.empty((1, 2, 1), order="F") for _ in ref]
+    with pytest.raises(ValueError):
+        lib.linsolve(A, b, x0, host_order="F", out=bad, **kw)
