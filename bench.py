@@ -444,8 +444,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list runs)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = BASELINE headline (default); cfg5 = batched n=28 chi=128 instances")
-    ap.add_argument("--instances", type=int, default=8, help="cfg5: instances per rank and step")
-    ap.add_argument("--streams", type=int, default=8, help="cfg5: concurrent contexts (CUDA streams) per rank")
+    ap.add_argument("--instances", type=int, default=24, help="cfg5: instances per rank and step")
+    ap.add_argument("--streams", type=int, default=12, help="cfg5: concurrent contexts (CUDA streams) per rank")
     ap.add_argument("--roofline-reps", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,6 +1,7 @@
 // extern "C" entry points of libqtt_b200.so (include/qtt_b200.h).  Plain pointers and sizes only; every C++ exception is
 // caught here and turned into a status code + message.
 #include "common.cuh"
+#include <atomic>
 #include <mutex>
 #include <set>
 #include <map>
@@ -22,6 +23,7 @@ struct PoolBlock { void* p; size_t bytes; cudaStream_t st; };
 struct DevicePool { std::multimap<size_t, PoolBlock> free_blocks; std::unordered_map<void*, size_t> live; size_t cached = 0; };
 std::mutex g_pool_mutex;
 std::set<cudaStream_t> g_live_streams;  // streams of live contexts (guarded by g_pool_mutex)
+std::atomic<int> g_live_ctx[64];         // live contexts per device: kernels that fill the whole GPU size themselves down when > 1
 std::map<int, DevicePool> g_pools;
 thread_local Ctx* tl_ctx = nullptr;
 
@@ -36,6 +38,8 @@ size_t pool_round(size_t bytes) {
   return (bytes + q - 1) / q * q;
 }
 }  // namespace
+
+int live_contexts(int device) { return (device >= 0 && device < 64) ? g_live_ctx[device].load() : 1; }
 
 void set_current_ctx(Ctx* c) { tl_ctx = c; }
 
@@ -228,6 +232,7 @@ qtt_ctx* qtt_ctx_create(int device) {
       std::lock_guard<std::mutex> lk(g_pool_mutex);
       g_live_streams.insert(c->stream);
     }
+    if (device >= 0 && device < 64) { g_live_ctx[device].fetch_add(1); c->counted = true; }
     QTT_CUDA(cudaMalloc(&c->d_scal, 16384 * sizeof(double)));
     QTT_CUDA(cudaMemset(c->d_scal, 0, 16384 * sizeof(double)));
     QTT_CUDA(cudaMalloc(&c->d_sync, 256 * sizeof(unsigned)));
@@ -258,6 +263,7 @@ void qtt_ctx_destroy(qtt_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) { pool_forget_stream(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->counted && c->device >= 0 && c->device < 64) g_live_ctx[c->device].fetch_sub(1);
   pool_trim();
   delete c;
 }

@@ -80,6 +80,7 @@ struct Ctx {
   unsigned dense_epoch = 0;  // value of the dense-QR panel barrier counter (d_sync + 240)
   unsigned bar_epoch = 0;  // value of the fused-Krylov barrier counter (d_sync + 4) after the launches so far
   unsigned gs_epoch = 0;   // value of the Gram-Schmidt select/re-orthogonalise barrier counter (d_sync + 232)
+  bool counted = false;    // this context is included in the per-device live-context count
   int qr_last_rank = -1, qr_last_need = 0;  // numerical rank / mindim of the last split: picks the QR variant that goes first (svd_qr.cu)
   bool profiling = false;
   // small device scratch for scalars / flags / partial reductions
@@ -122,6 +123,10 @@ inline void check_launch(Ctx* c, const char* what) {
 // Launch with programmatic stream serialisation: the launch of a short kernel is processed while its predecessor in the
 // stream drains (measured on the Arnoldi chain: -1.7 us per launch, 110.4 -> 107.3 ms per sweep).  The kernel MUST begin
 // with dev::pdl_wait().  QTT_PDL=0 falls back to plain launches.
+// live contexts on a device (capi.cu): with several of them (batch.py / bench.py --workload cfg5: one context = one stream per
+// host thread) kernels that would fill the whole GPU by themselves use smaller grids so that the streams overlap
+int live_contexts(int device);
+
 template <typename... P, typename... A>
 inline void launch_pdl(Ctx* ctx, const char* what, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A... args) {
   static const bool on = !(getenv("QTT_PDL") && atoi(getenv("QTT_PDL")) == 0);

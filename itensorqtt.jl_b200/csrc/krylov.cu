@@ -561,7 +561,11 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   QTT_REQUIRE(k >= 1 && k <= 64, "kry_cgs2_fused: k out of range");
   // one CTA per >= 512 elements: short vectors (edge / mid bonds) use few CTAs, whose grid barriers are cheaper (measured
   // at len = 16384 / 65536, k = 30: 25.2 / 27.7 us with 512, 30.3 / 31.8 us with 1024, no gain below 512)
-  static const int min_per = getenv("QTT_CGS2_MINPER") ? atoi(getenv("QTT_CGS2_MINPER")) : 512;
+  // With several live contexts on the device (independent instances on their own streams) a grid of up to 148 CTAs with a full
+  // SM of shared memory each serialises the streams: one CTA per >= 2048 elements lets four of these kernels run side by side
+  // (measured, 8 streams of n = 28, chi = 128 instances: 19.3 -> 31.3 instances/s; 4096: 29.3).
+  static const int min_per_env = getenv("QTT_CGS2_MINPER") ? atoi(getenv("QTT_CGS2_MINPER")) : 0;
+  const int min_per = min_per_env > 0 ? min_per_env : (live_contexts(ctx->device) > 1 ? 2048 : 512);
   int G = (int)((len + min_per - 1) / min_per);
   if (G > ctx->sms) G = ctx->sms;
   if (G < 1) G = 1;
