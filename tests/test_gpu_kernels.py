@@ -37,6 +37,10 @@ def test_gemm_transposed_layouts(lib, shape):
 CASES = [  # (chil, chir, wl, wm, wr)
     (4, 4, 3, 3, 3), (32, 32, 3, 3, 3), (16, 8, 5, 5, 5), (1, 2, 1, 3, 3), (2, 1, 3, 3, 1), (7, 5, 4, 3, 2),
     (128, 128, 4, 4, 4), (64, 96, 3, 5, 4), (3, 3, 9, 2, 6),
+    # TMA-staged kernels (even bond dimensions): ragged edges are zero-filled by the TMA unit; K_B takes its TMA kernel for
+    # single-wave grids only (4 chil / 32 x chir / 64 tiles between 112 and 148)
+    (250, 254, 3, 3, 3), (256, 230, 3, 3, 3), (254, 256, 6, 2, 8), (130, 258, 2, 3, 5), (192, 320, 1, 2, 3), (18, 6, 5, 4, 3),
+    (255, 257, 3, 3, 3),   # odd dimensions: tensor maps need 16-byte strides, the cp.async kernels take over
 ]
 
 
