@@ -94,3 +94,64 @@ def test_matvec_matches_dense_operator():
     T = O.effective_operator_dense(L, W1, W2, R)
     assert np.allclose(T @ v.reshape(-1), O.matvec2(L, W1, W2, R, v).reshape(-1))
     assert O.matvec2_flops(256, 256, 3, 3, 3) == 4 * 3 * 4 * 256 ** 3 + 4 * 9 * 8 * 256 ** 2
+
+
+def _captured_local_problem(n=8, chi=6, bond=3, seed=4):
+    """The projected two-site problem of an Airy chain at one bond, as the sweep sees it: dense effective operator, projected
+    right-hand side, current two-site tensor (reference src/linsolve.jl:13-22, 71-75)."""
+    from oracle.core import orthogonalize
+    from oracle.sweep import env_left_update, env_right_update, benv_left_update, benv_right_update, effective_operator_dense, project_rhs
+    A, b, _, _ = _airy(n)
+    x = orthogonalize(O.random_mps(n, chi, seed), bond)
+    one3, one2 = np.ones((1, 1, 1)), np.ones((1, 1))
+    L, Lb = one3, one2
+    for i in range(bond):
+        L, Lb = env_left_update(L, x[i], A[i]), benv_left_update(Lb, x[i], b[i])
+    R, Rb = one3, one2
+    for i in range(n - 1, bond + 1, -1):
+        R, Rb = env_right_update(R, x[i], A[i]), benv_right_update(Rb, x[i], b[i])
+    T = effective_operator_dense(L, A[bond], A[bond + 1], R)
+    rhs = project_rhs(Lb, b[bond], b[bond + 1], Rb).reshape(-1)
+    phi = np.tensordot(x[bond], x[bond + 1], axes=([2], [0])).reshape(-1)
+    return T, rhs, phi
+
+
+def test_gmres_cycle_is_the_krylov_minimiser_and_matches_scipy():
+    """Hardening of the (Julia-unpinned) KrylovKit restatement on captured local problems of a sweep: after ONE cycle of k
+    Arnoldi steps from x0, GMRES returns THE minimiser of |b - (a0 + a1 T) x| over x0 + K_k(r0) -- unique, independent of the
+    orthogonalisation scheme and of how the shift is folded in.  Checked against (1) an explicit least-squares solve on the
+    power basis of the Krylov space and (2) scipy.sparse.linalg.gmres with restart = k, one outer iteration."""
+    import scipy.sparse.linalg as sla
+    for bond, a0, a1, k in ((3, 0.0, 1.0, 6), (2, -0.37, 1.0, 9), (4, 0.8, -1.3, 5)):
+        T, rhs, phi = _captured_local_problem(bond=bond)
+        N = T.shape[0]
+        Aeff = a0 * np.eye(N) + a1 * T
+        x, info = O.gmres_krylovkit(lambda v: T @ v, rhs, phi, a0, a1, fixed_matvecs=k)
+        assert info["numops"] == k + 1
+        r0 = rhs - Aeff @ phi
+        K = np.empty((N, k))
+        v = r0 / np.linalg.norm(r0)
+        for j in range(k):       # orthonormalised power basis (QR keeps it well conditioned)
+            K[:, j] = v
+            v = Aeff @ v
+            v -= K[:, : j + 1] @ (K[:, : j + 1].T @ v)
+            v /= np.linalg.norm(v)
+        y = np.linalg.lstsq(Aeff @ K, r0, rcond=None)[0]
+        x_min = phi + K @ y
+        scale = np.linalg.norm(x_min)
+        assert np.linalg.norm(x - x_min) < 1e-10 * scale
+        xs, _ = sla.gmres(Aeff, rhs, x0=phi, rtol=1e-300, atol=0.0, restart=k, maxiter=1)
+        assert np.linalg.norm(x - xs) < 1e-9 * scale
+        # the residual estimate the solver reports is the true residual of its iterate
+        assert abs(info["normres"] - np.linalg.norm(rhs - Aeff @ x)) < 1e-9 * np.linalg.norm(rhs)
+
+
+def test_gmres_converged_mode_matches_dense_solve_on_local_problem():
+    """tol mode (the reference's linsolve_kwargs: tol, krylovdim, maxiter with restarts): converges to the dense solution of the
+    captured local problem, restart residual recomputed from the operator."""
+    T, rhs, phi = _captured_local_problem(bond=3)
+    a0, a1 = 0.25, 1.0
+    Aeff = a0 * np.eye(T.shape[0]) + a1 * T
+    x, info = O.gmres_krylovkit(lambda v: T @ v, rhs, phi, a0, a1, tol=1e-11, krylovdim=12, maxiter=200)
+    assert info["converged"] == 1
+    assert np.linalg.norm(x - np.linalg.solve(Aeff, rhs)) < 1e-8 * np.linalg.norm(x)
