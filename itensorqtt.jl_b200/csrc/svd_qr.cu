@@ -2421,6 +2421,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     // panels over the working rows W (nrows x ldp) until `rmax` basis rows exist or nothing above the threshold is left
     auto run_panels = [&](double* W, int nrows, double* nrm, int* rst, int rmax, int r_have, bool main_phase, double thr_fixed) -> bool {
       const int nominal = (rmax - r_have + GSB - 1) / GSB;
+      const int hint_panels = (main_phase && ctx->qr_last_need == need && ctx->qr_last_rank > 0) ? (ctx->qr_last_rank + 21) / 22 + 1 : 0;
       // fused selection + second Gram-Schmidt pass (one cooperative launch of 32 CTAs) when its staging fits in shared memory
       const int cw2 = (ldp / 2 + GSB - 1) / GSB;
       const size_t qs_d = std::max((size_t)((kmax + GSB - 1) / GSB) * pld, (size_t)kmax * 2 * cw2);
@@ -2493,7 +2494,11 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
           else launch_pdl(ctx, "gs_update", gs_update_kernel<24>, dim3(ug), dim3(256), usm, W, nrows, p, ldp, (const int*)rst, nrm, Y, qd, ldy, wr, (const QrCtl*)ctl);
         }
         const int np1 = pn + 1;
-        if ((np1 & (np1 - 1)) == 0 || np1 >= nominal) {   // 1, 2, 4, 8, ... panels, then every panel: has the factorisation finished?
+        // has the factorisation finished?  Every poll drains the stream, so the first one waits for the number of panels the
+        // previous split of this shape needed (ranks vary smoothly along a chain: ~22 rows are accepted per panel), then every
+        // second panel; without a hint: after 1, 2, 4, 8, ... panels.  Panels launched after `done` are no-ops (~3 us each).
+        const bool poll = hint_panels > 0 ? (np1 >= hint_panels && ((np1 - hint_panels) % 2 == 0)) : ((np1 & (np1 - 1)) == 0);
+        if (poll || np1 >= nominal) {
           QTT_CUDA(cudaMemcpyAsync(h_done, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
           QTT_CUDA(cudaStreamSynchronize(ctx->stream));
           if (*h_done) return true;
