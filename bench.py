@@ -17,7 +17,9 @@ measured FP64 DMMA peak; `cpu_baseline` = the numpy/OpenBLAS oracle port on the 
 Protocol: the state after W warm-up sweeps is cloned; the device-resident leg and the host-buffer leg each run sweeps
 W+1 ... W+K chained from that clone (the per-sweep cost depends on the sweep index while the numerical rank of the
 state fills in, so both legs must cover the same sweeps); `ms_per_step_list` holds the per-sweep times of both.
-At N > 1 every rank solves an independent instance (wavenumber k_i): weak scaling, NCCL only gathers residuals.
+At N > 1 every rank runs an independent REPLICA of the same instance (a sweep is sequential and does not shard, DESIGN.md
+section 6): weak scaling, NCCL only gathers residuals and timings.  (`--workload cfg5` is the configuration whose units --
+independent wavenumber instances -- do shard over ranks.)
 `--impl reference` times whole sweeps of the CPU port with every host core (thread count set explicitly).
 """
 import argparse
@@ -64,8 +66,10 @@ def workload(rank=0, n=N_BITS, chi=CHI, nk=NK):
     """Operands as host cores (package builders; the oracle is not involved)."""
     import itensorqtt_jl_b200 as q
     A = q.laplacian_mpo(n, 1.0)
-    # independent instances at N > 1: wavenumber k_i = 2 pi (2^nk + rank)  (SURVEY.md 8d cfg 5 recipe)
-    lam = -((2 * np.pi * (2.0 ** nk + rank) / 2.0 ** n) ** 2)
+    # N > 1: replicas of the SAME instance.  (Round 1 gave rank r the wavenumber 2 pi (2^nk + r); the split's cost depends on the
+    # numerical rank of the evolving state, so different wavenumbers differ by +-10 % per sweep and the max over ranks measured
+    # that workload spread, not the scaling of the system.)
+    lam = -((2 * np.pi * (2.0 ** nk) / 2.0 ** n) ** 2)
     b = q.boundary_value_mps(n, 1 / np.sqrt(2), 1 / np.sqrt(2))
     x0 = q.random_mps(n, chi, 2)   # a wavenumber sweep starts every k from the same guess: equal work per rank by construction
     return A, b, x0, lam
@@ -267,7 +271,7 @@ def run_ours(args):
         "config": {"workload": "Helmholtz QTT linsolve n=%d chi=%d (BASELINE configs[1]): laplacian_mpo w=3, a0=-lambda (nk=%d), "
                                "maxdim=mindim=%d, cutoff=0, fixed-work GMRES %d Arnoldi steps/bond" % (n, chi, args.nk, chi, args.krylov),
                    "bonds_per_sweep": 2 * (n - 1), "matvecs_per_sweep": int(infos[-1]["matvecs"]),
-                   "instances": world, "instance_rule": "rank r solves wavenumber k_r = 2 pi (2^nk + r) from the same start vector",
+                   "instances": world, "instance_rule": "replicas: every rank solves the same instance (k = 2 pi 2^nk) from the same start vector",
                    "ms_per_step_per_rank": [float(v) for v in allt[:, 0]],
                    "ms_per_step_list": {"device_resident_rank0": dev_list, "e2e_rank0": e2e_list},
                    "protocol": "sweeps W+1..W+K chained from the state after W warm-up sweeps; the e2e leg repeats the same K sweeps "
