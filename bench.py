@@ -321,11 +321,12 @@ def run_cfg5(args):
     ctxs = [q.Context(local) for _ in range(T)]
     dev = [(q.DeviceMPO(A, c), q.DeviceMPS(b, c)) for c in ctxs]
     x0 = q.random_mps(n, chi, 2)
+    dx0 = [q.DeviceMPS(x0, c) for c in ctxs]   # the common start guess lives on the device like A and b (linsolve clones it)
 
     def solve(i, t):
         k = 2 * np.pi * (2 ** 16 + i * world + rank)       # global instance id i * world + rank
         lam = -((k / 2 ** n) ** 2)
-        x, info = q.linsolve(dev[t][0], dev[t][1], x0, -lam, 1.0, nsweeps=2, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
+        x, info = q.linsolve(dev[t][0], dev[t][1], dx0[t], -lam, 1.0, nsweeps=2, maxdim=chi, mindim=chi, cutoff=0.0, fixed_matvecs=args.krylov,
                              x0_canonical=True, ctx=ctxs[t], return_info=True, on_device=True)
         x.free()
         return info[-1]["solver_resid"]
