@@ -126,6 +126,12 @@ inline void check_launch(Ctx* c, const char* what) {
 // live contexts on a device (capi.cu): with several of them (batch.py / bench.py --workload cfg5: one context = one stream per
 // host thread) kernels that would fill the whole GPU by themselves use smaller grids so that the streams overlap
 int live_contexts(int device);
+// this context is the only one alive on its device: kernels with hand-rolled grid barriers may be launched non-cooperatively
+// (all their CTAs become resident because nothing else holds SMs); QTT_COOP_ALWAYS=1 disables
+inline bool sole_context(const Ctx* ctx) {
+  static const bool always = getenv("QTT_COOP_ALWAYS") != nullptr && atoi(getenv("QTT_COOP_ALWAYS")) != 0;
+  return !always && live_contexts(ctx->device) == 1;
+}
 
 template <typename... P, typename... A>
 inline void launch_pdl(Ctx* ctx, const char* what, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A... args) {

@@ -332,6 +332,7 @@ __device__ __forceinline__ void slice_axpys(const Cgs2Args& a, double* ws, const
 
 constexpr int FT_MAX = 512;
 __global__ void __launch_bounds__(FT_MAX) cgs2_fused_kernel(Cgs2Args a) {
+  dev::pdl_wait();   // no-op unless launched with programmatic stream serialisation
   extern __shared__ double dyn[];
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[13] = a.dbg[11];  // end stamp of the previous launch
   stamp(a, 12);
@@ -612,12 +613,16 @@ void kry_cgs2_fused(Ctx* ctx, const double* V, int k, size_t len, double* w, dou
   a.off_h1 = off_h1; a.off_h2 = off_h2; a.off_nres2 = off_nres2; a.off_done = off_done;
   // cooperative launch: the grid barriers need every CTA resident (measured: no extra launch cost over <<< >>>)
   void* args[] = {&a};
-  static const bool plain_launch = getenv("QTT_CGS2_PLAIN") != nullptr;
-  if (plain_launch) {
-    cgs2_fused_kernel<<<G, fthreads, smem, ctx->stream>>>(a);
-    QTT_CUDA(cudaGetLastError());
+  // The grid barriers need every CTA resident.  A cooperative launch guarantees it but cannot overlap the tail of the previous
+  // kernel (measured: ~6.5 us between two cooperative launches).  When this context is the only one alive on the device nothing
+  // else competes for the SMs -- the <= 148 CTAs (one per SM) become resident as matvec_b drains -- so the kernel is launched
+  // with programmatic stream serialisation instead (it starts with griddepcontrol.wait): Krylov phase 73.0 -> 70.4 ms per sweep,
+  // 20.6 -> 18.5 us per step at k = 1.  With several live contexts (concurrent streams of independent instances) two partially
+  // resident spinning grids could block each other: those keep the cooperative launch.  QTT_COOP_ALWAYS=1 forces it.
+  if (sole_context(ctx)) {
+    launch_pdl(ctx, "cgs2_fused", cgs2_fused_kernel, dim3(G), dim3(fthreads), smem, a);
+    ctx->launches--;   // (launch_pdl counts; the common tail below counts again)
   } else {
-    // (programmatic launch behind matvec_b was measured: no gain, 107.1 vs 107.2 ms per sweep)
     QTT_CUDA(cudaLaunchCooperativeKernel((void*)cgs2_fused_kernel, dim3(G), dim3(fthreads), args, smem, ctx->stream));
   }
   ctx->launches++;

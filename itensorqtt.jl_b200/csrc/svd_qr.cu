@@ -1518,6 +1518,7 @@ __global__ void __launch_bounds__(256) gs_select_reorth_kernel(const double* __r
                                                                const int* __restrict__ rowstate, double* __restrict__ Pbuf, QrCtl* ctl,
                                                                const double* __restrict__ Yq, int ldy, double* __restrict__ Cbuf,
                                                                unsigned* bar, unsigned epoch, int pld) {
+  dev::pdl_wait();   // no-op unless launched with programmatic stream serialisation (sole context, see the launch site)
   extern __shared__ __align__(16) double ssm[];
   double* cand = ssm;                                   // [q rounded up to even]
   double* Ps = ssm + ((q + 1) & ~1);                    // [GSB][pld] the selected rows; after the barrier: C^T [GSB][pld]
@@ -2438,9 +2439,14 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
           int nr = nrows, pp = p, lp = ldp, rm = rmax, ly = ldy;
           double tf = thr_fixed;
           int pl = pld;
-          void* args[] = {&Wc, &nr, &pp, &lp, &rm, &zt2, &first, &tf, &nc, &rc, &Pbuf, &ctl, &yq, &ly, &Ct, &bar, &epoch, &pl};
-          QTT_CUDA(cudaLaunchCooperativeKernel((void*)gs_select_reorth_kernel, dim3(GSB), dim3(256), args, fsm, ctx->stream));
-          ctx->launches++;
+          if (sole_context(ctx)) {   // 32 CTAs: resident together whenever nothing else competes for the SMs (krylov.cu has the argument)
+            launch_pdl(ctx, "gs_select_reorth", gs_select_reorth_kernel, dim3(GSB), dim3(256), fsm, Wc, nr, pp, lp, rm, zt2, first, tf, nc, rc, Pbuf, ctl,
+                       yq, ly, Ct, bar, epoch, pl);
+          } else {
+            void* args[] = {&Wc, &nr, &pp, &lp, &rm, &zt2, &first, &tf, &nc, &rc, &Pbuf, &ctl, &yq, &ly, &Ct, &bar, &epoch, &pl};
+            QTT_CUDA(cudaLaunchCooperativeKernel((void*)gs_select_reorth_kernel, dim3(GSB), dim3(256), args, fsm, ctx->stream));
+            ctx->launches++;
+          }
           ctx->gs_epoch += (unsigned)GSB;
         } else {
         launch_pdl(ctx, "gs_select", gs_select_kernel, dim3(GSB), dim3(256), sizeof(double) * nrows, (const double*)W, nrows, p, ldp, rmax, zt * zt,
