@@ -897,6 +897,7 @@ __device__ __forceinline__ void apply_cross(double (&xp)[NC][B / 2], double (&xm
 
 template <int B>
 __global__ void __launch_bounds__(GNT, 1) jacobi_gram_kernel(GjArgs ga) {
+  dev::pdl_wait();   // no-op unless launched with programmatic stream serialisation (sole context)
   using K = GG<B>;
   constexpr int GR = K::R, GLD = K::LD, GJLD = K::JLD, H = K::H, NC = K::NC;
   constexpr int GAC = (GAT / 2) * NC;   // slab columns the register warps hold at a time
@@ -1378,8 +1379,13 @@ bool launch_jq_gram_b(Ctx* ctx, JqArgs& a, int r) {
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeCooperative;
-  at[1].val.cooperative = 1;
+  if (sole_context(ctx)) {   // nothing else competes for the SMs: all clusters become resident (krylov.cu has the argument)
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+  } else {
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+  }
   cfg.attrs = at; cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, jacobi_gram_kernel<B>, ga);
   if (e != cudaSuccess) fail(QTT_ERR_CUDA, "jacobi_gram launch failed (%d clusters x %d): %s", ncl, cs, cudaGetErrorString(e));
