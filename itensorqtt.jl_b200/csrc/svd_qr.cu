@@ -2398,6 +2398,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   const size_t gs_smem = ((size_t)GSB * pld + 2 * GSB * (GSB + 1) + GSB * (GSB + 4)) * sizeof(double);
   int need = mindim < kmax ? mindim : kmax;   // basis rows the truncation rule may keep whatever the spectrum
   bool gs_done = false;
+  int known_r = -1;   // rank known on the host without a read-back (Gram-Schmidt path, no completion phase)
   if (!gs_off && p % 2 == 0 && kmax >= 64 && gs_smem <= 220 * 1024) {
     static DevOnce gs_once;
     gs_once.run(ctx->device, [&] {
@@ -2512,6 +2513,7 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
         const bool poll = hint_panels > 0 ? (np1 >= hint_panels && ((np1 - hint_panels) % 2 == 0)) : ((np1 & (np1 - 1)) == 0);
         if (poll || np1 >= nominal) {
           QTT_CUDA(cudaMemcpyAsync(h_done, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+          QTT_CUDA(cudaMemcpyAsync(h_done + 1, &ctl->r_next, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));   // the rank, once done
           QTT_CUDA(cudaStreamSynchronize(ctx->stream));
           if (*h_done) return true;
         }
@@ -2534,9 +2536,8 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
     if (gs_done) {
       launch_pdl(ctx, "gs_commit", gs_commit_kernel, dim3(1), dim3(32), 0, ctl, 0);
       int* h_r = reinterpret_cast<int*>(ctx->h_scal + 16);
-      QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-      const int r_num = *h_r;
+      const int r_num = h_done[1];   // ctl->r_next as read by the poll that saw `done` (= ctl->r after the commit): no extra round trip
+      if (r_num >= need) { known_r = r_num; }   // no completion phase: the Jacobi launch below needs no read-back either
       ctx->qr_last_rank = r_num;
       ctx->qr_last_need = need;
       if (r_num < need) {
@@ -2634,10 +2635,13 @@ RowSvd svd_rows_qr(Ctx* ctx, const double* M, int q, int p, double cutoff, int m
   if (!gram_off && kmax >= 64 && kmax <= 2048) {
     // the grid and the block size follow the numerical rank: one 4-byte read-back (the split synchronises for the kept rank anyway)
     int* h_r = reinterpret_cast<int*>(ctx->h_scal + 16);
-    QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    QTT_CUDA(cudaMemcpyAsync(h_r + 1, &ctl->rj, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    QTT_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int r_rot = h_r[1] > 0 ? h_r[1] : h_r[0];
+    int r_rot = known_r;
+    if (r_rot < 0) {
+      QTT_CUDA(cudaMemcpyAsync(h_r, &ctl->r, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      QTT_CUDA(cudaMemcpyAsync(h_r + 1, &ctl->rj, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      QTT_CUDA(cudaStreamSynchronize(ctx->stream));
+      r_rot = h_r[1] > 0 ? h_r[1] : h_r[0];
+    }
     if (r_rot >= 32) launched = launch_jq_gram(ctx, a, r_rot);
   }
   if (launched) {
