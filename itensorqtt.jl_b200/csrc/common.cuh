@@ -127,7 +127,10 @@ inline void check_launch(Ctx* c, const char* what) {
 // host thread) kernels that would fill the whole GPU by themselves use smaller grids so that the streams overlap
 int live_contexts(int device);
 // this context is the only one alive on its device: kernels with hand-rolled grid barriers may be launched non-cooperatively
-// (all their CTAs become resident because nothing else holds SMs); QTT_COOP_ALWAYS=1 disables
+// (all their CTAs become resident because nothing else holds SMs); QTT_COOP_ALWAYS=1 disables.  Why it is safe on ONE stream: a
+// programmatically launched grid starts only after every CTA of its predecessor has exited or triggered
+// (griddepcontrol.launch_dependents); the only kernels that trigger are matvec_a(_tma), whose successor is always matvec_b (no
+// barrier), so a barrier kernel finds an empty GPU, and its own successor cannot start before all of its CTAs have exited.
 inline bool sole_context(const Ctx* ctx) {
   static const bool always = getenv("QTT_COOP_ALWAYS") != nullptr && atoi(getenv("QTT_COOP_ALWAYS")) != 0;
   return !always && live_contexts(ctx->device) == 1;
