@@ -159,6 +159,56 @@ __device__ __forceinline__ bool rotate_pair_cplx(double* __restrict__ ar, double
   return true;
 }
 
+// the same with both rows held in registers between the inner products and the update (ld <= 64 NC): one pass over L2 instead of
+// two (the rounds of the complex density matrices of `apply` are latency-bound: a round is a barrier plus these passes)
+template <int NC>
+__device__ __forceinline__ bool rotate_pair_cplx_reg(double* __restrict__ ar, double* __restrict__ ai, double* __restrict__ br,
+                                                     double* __restrict__ bi, int ld, double tol, double thr, int lane) {
+  double2 xr[NC], xi[NC], yr[NC], yi[NC];
+  double alpha = 0.0, beta = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      xr[k] = __ldcg(reinterpret_cast<const double2*>(ar + col)); xi[k] = __ldcg(reinterpret_cast<const double2*>(ai + col));
+      yr[k] = __ldcg(reinterpret_cast<const double2*>(br + col)); yi[k] = __ldcg(reinterpret_cast<const double2*>(bi + col));
+    } else {
+      xr[k] = xi[k] = yr[k] = yi[k] = make_double2(0.0, 0.0);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    alpha += xr[k].x * xr[k].x + xi[k].x * xi[k].x + xr[k].y * xr[k].y + xi[k].y * xi[k].y;
+    beta += yr[k].x * yr[k].x + yi[k].x * yi[k].x + yr[k].y * yr[k].y + yi[k].y * yi[k].y;
+    gr += xr[k].x * yr[k].x + xi[k].x * yi[k].x + xr[k].y * yr[k].y + xi[k].y * yi[k].y;  // Re(x conj(y))
+    gi += xi[k].x * yr[k].x - xr[k].x * yi[k].x + xi[k].y * yr[k].y - xr[k].y * yi[k].y;  // Im(x conj(y))
+  }
+  alpha = warp_sum(alpha);
+  beta = warp_sum(beta);
+  gr = warp_sum(gr);
+  gi = warp_sum(gi);
+  if (!(alpha > thr) || !(beta > thr)) return false;
+  const double gabs = hypot(gr, gi);
+  const double lim = sqrt(alpha) * sqrt(beta);
+  if (!(lim > 0.0) || !(gabs > tol * lim)) return false;
+  double c, s;
+  rotation(alpha, beta, gabs, c, s);
+  const double wr = gr / gabs, wi = gi / gabs;  // phase omega
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int col = 2 * lane + 64 * k;
+    if (col < ld) {
+      const double2 tr = make_double2(wr * yr[k].x - wi * yi[k].x, wr * yr[k].y - wi * yi[k].y);   // y~ = omega * y
+      const double2 ti = make_double2(wr * yi[k].x + wi * yr[k].x, wr * yi[k].y + wi * yr[k].y);
+      __stcg(reinterpret_cast<double2*>(ar + col), make_double2(c * xr[k].x - s * tr.x, c * xr[k].y - s * tr.y));
+      __stcg(reinterpret_cast<double2*>(ai + col), make_double2(c * xi[k].x - s * ti.x, c * xi[k].y - s * ti.y));
+      __stcg(reinterpret_cast<double2*>(br + col), make_double2(s * xr[k].x + c * tr.x, s * xr[k].y + c * tr.y));
+      __stcg(reinterpret_cast<double2*>(bi + col), make_double2(s * xi[k].x + c * ti.x, s * xi[k].y + c * ti.y));
+    }
+  }
+  return true;
+}
+
 __device__ __forceinline__ double row_norm2(const JacobiArgs& a, int i, int lane) {
   const double* ri = a.Z + (size_t)i * a.ld;
   double acc = 0.0;
@@ -176,7 +226,8 @@ __device__ __forceinline__ double row_norm2(const JacobiArgs& a, int i, int lane
   return warp_sum(acc);
 }
 
-// NCH > 0: real rows held in registers; NCH == 0: real rows, two passes; NCH == -1: complex rows (planar), two passes
+// NCH > 0: real rows held in registers; NCH == 0: real rows, two passes; NCH == -1: complex rows (planar), two passes;
+// NCH < -1: complex rows held in registers (-NCH chunks of 64 columns)
 // CL: the whole grid is ONE thread-block cluster (<= 8 CTAs of 8 warps) and the per-round barrier is the hardware cluster
 // barrier (release / acquire at cluster scope; the rows are accessed with .cg loads / stores, i.e. at L2) instead of the
 // software grid barrier: the rounds of a small 2k x 2k density matrix are barrier-bound (profiles/r01_launches_apply_dft.md).
@@ -236,7 +287,8 @@ __global__ void __launch_bounds__(CL ? 256 : 64) jacobi_rows_kernel(JacobiArgs a
         bool rot;
         if constexpr (NCH > 0) rot = rotate_pair_reg<NCH>(ra, rb, a.ld, a.tol, thr, lane);
         else if constexpr (NCH == 0) rot = rotate_pair_mem(ra, rb, a.ld, a.tol, thr, lane);
-        else rot = rotate_pair_cplx(ra, a.Zi + (size_t)ia * a.ld, rb, a.Zi + (size_t)ib * a.ld, a.ld, a.tol, thr, lane);
+        else if constexpr (NCH == -1) rot = rotate_pair_cplx(ra, a.Zi + (size_t)ia * a.ld, rb, a.Zi + (size_t)ib * a.ld, a.ld, a.tol, thr, lane);
+        else rot = rotate_pair_cplx_reg<-NCH>(ra, a.Zi + (size_t)ia * a.ld, rb, a.Zi + (size_t)ib * a.ld, a.ld, a.tol, thr, lane);
         rotated |= rot;
       }
       bar();
@@ -376,7 +428,12 @@ RowSvd svd_rows_ex(Ctx* ctx, const double* M, const double* Mi, int q, int p, do
     cl = (npairs + 7) / 8;
     if (cl > 8) cl = 8;
   }
-  if (cplx) launch_jacobi<-1>(ctx, a, grid, cl);
+  if (cplx) {   // complex rows: in registers up to 512 columns (NCH = -(chunks of 64 columns)), two passes beyond
+    if (ld <= 128) launch_jacobi<-2>(ctx, a, grid, cl);
+    else if (ld <= 256) launch_jacobi<-4>(ctx, a, grid, cl);
+    else if (ld <= 512) launch_jacobi<-8>(ctx, a, grid, cl);
+    else launch_jacobi<-1>(ctx, a, grid, cl);
+  }
   else if (ld <= 128) launch_jacobi<2>(ctx, a, grid, cl);
   else if (ld <= 256) launch_jacobi<4>(ctx, a, grid, cl);
   else if (ld <= 512) launch_jacobi<8>(ctx, a, grid, cl);
