@@ -2004,7 +2004,7 @@ __global__ void __launch_bounds__(GST) gs_panel_cluster_kernel(const double* __r
         Lm[i1 * LD + t] = i1 >= t ? g1 * inv : 0.0;
         if (i0 == 0) { invd[t] = inv; acc[t] = ok ? 1 : 0; }
       }
-      __syncthreads();
+      // (no barrier here: everything read above lies in column t, which the update below never writes)
       if (j > t) {
         if (i0 > t) Gs[i0 * LD + j] -= g0 * gjt * inv2;
         if (i1 > t) Gs[i1 * LD + j] -= g1 * gjt * inv2;
